@@ -1,0 +1,136 @@
+// Fused attention / MLP blocks behind make_q_attn / q_attn_forward_1 / q_attn_forward_2 (ext_qattn.cpp:24-191,
+// cuda/q_attn.cu:153-345) and make_q_mlp / q_mlp_forward_ (ext_qmlp.cpp:22-118, cuda/q_mlp.cu:78-236).
+//
+// Kernel count per decoder layer (decode):   reference            here
+//   attn part 1   norm, Q, K, V, rope        5 launches           2  (norm+QKV in one GEMV launch, rope)
+//   attn part 2   O (+residual via atomics)  1                    1  (residual add in the epilogue)
+//   mlp           norm, gate, up, act, down  5                    2  (norm+gate|up+silu*mul, down+residual)
+// All launches carry the programmatic-dependent-launch attribute, so a whole decode step captured in one CUDA
+// graph (exllamav2_b200/model.py) streams weights back to back.
+#include "gemv.cuh"
+
+namespace exl2b {
+
+int rope_launch(cudaStream_t stream, half* x, const half* sin, const half* cos, int batch, int rows_per_batch, int head_dim,
+                int num_heads, int past_len, const int32_t* past_lens, int neox, int sincos_size);
+
+struct QAttn {
+    exl2b_qattn_desc d;
+    int device;
+};
+struct QMlp {
+    exl2b_qmlp_desc d;
+    int device;
+};
+
+static GemvMat make_mat(const QMatrix* q, const half* x, int ldx, half* c, int ldc, int clear) {
+    GemvMat m = {};
+    m.w = q->v;
+    m.x = x;
+    m.ldx = ldx;
+    m.c = c;
+    m.ldc = ldc;
+    m.clear = clear;
+    return m;
+}
+
+}  // namespace exl2b
+
+using namespace exl2b;
+
+extern "C" int exl2b_qattn_create(const exl2b_qattn_desc* d, exl2b_qattn_t* out) {
+    EXL2B_REQUIRE(d && out, "null argument");
+    EXL2B_REQUIRE(d->q_proj && d->k_proj && d->v_proj && d->o_proj, "q/k/v/o handles are required");
+    const QMatrix *q = (const QMatrix*)d->q_proj, *k = (const QMatrix*)d->k_proj, *v = (const QMatrix*)d->v_proj,
+                  *o = (const QMatrix*)d->o_proj;
+    EXL2B_REQUIRE(q->v.K == d->hidden_size && k->v.K == d->hidden_size && v->v.K == d->hidden_size, "q/k/v_proj is wrong shape");
+    EXL2B_REQUIRE(o->v.N == d->hidden_size, "o_proj is wrong shape");          // ext_qattn.cpp:67
+    EXL2B_REQUIRE(q->v.N == d->num_heads * d->head_dim && k->v.N == d->num_kv_heads * d->head_dim && v->v.N == k->v.N,
+                  "projection widths do not match the head layout");
+    EXL2B_REQUIRE(q->device == k->device && q->device == v->device && q->device == o->device, "handles on different devices");
+    QAttn* a = new QAttn{*d, q->device};
+    *out = (exl2b_qattn_t)a;
+    return 0;
+}
+
+extern "C" int exl2b_qattn_destroy(exl2b_qattn_t h) {
+    delete (QAttn*)h;
+    return 0;
+}
+
+extern "C" int exl2b_qattn_forward_1(exl2b_qattn_t h, const uint16_t* x, int batch, int q_len, int past_len,
+                                     const int32_t* past_lens, uint16_t* q, uint16_t* k, uint16_t* v, const uint16_t* sin,
+                                     const uint16_t* cos, exl2b_stream_t stream_) {
+    QAttn* a = (QAttn*)h;
+    EXL2B_REQUIRE(a && x && q && k && v, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EXL2B_CUDA(cudaSetDevice(a->device));
+    const exl2b_qattn_desc& d = a->d;
+    const int rows = batch * q_len;
+    const QMatrix *mq = (const QMatrix*)d.q_proj, *mk = (const QMatrix*)d.k_proj, *mv = (const QMatrix*)d.v_proj;
+    GemvMat mats[3] = {
+        make_mat(mq, (const half*)x, d.hidden_size, (half*)q, mq->v.N, 1),
+        make_mat(mk, (const half*)x, d.hidden_size, (half*)k, mk->v.N, 1),
+        make_mat(mv, (const half*)x, d.hidden_size, (half*)v, mv->v.N, 1),
+    };
+    int rc = gemv_launch(a->device, stream, mats, 3, rows, (const half*)d.layernorm, d.norm_epsilon, EPI_STORE);
+    if (rc) return rc;
+    if (d.rope_style != 0) {
+        EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
+        const int neox = d.rope_style == 2;
+        rc = rope_launch(stream, (half*)q, (const half*)sin, (const half*)cos, batch, q_len * d.num_heads, d.head_dim, d.num_heads,
+                         past_len, past_lens, neox, d.sincos_size);
+        if (rc) return rc;
+        rc = rope_launch(stream, (half*)k, (const half*)sin, (const half*)cos, batch, q_len * d.num_kv_heads, d.head_dim,
+                         d.num_kv_heads, past_len, past_lens, neox, d.sincos_size);
+    }
+    return rc;
+}
+
+extern "C" int exl2b_qattn_forward_2(exl2b_qattn_t h, uint16_t* x, const uint16_t* attn_out, int batch, int q_len,
+                                     exl2b_stream_t stream) {
+    QAttn* a = (QAttn*)h;
+    EXL2B_REQUIRE(a && x && attn_out, "null argument");
+    EXL2B_CUDA(cudaSetDevice(a->device));
+    const QMatrix* mo = (const QMatrix*)a->d.o_proj;
+    GemvMat m = make_mat(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, a->d.has_residual ? 0 : 1);
+    return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
+}
+
+extern "C" int exl2b_qmlp_create(const exl2b_qmlp_desc* d, exl2b_qmlp_t* out) {
+    EXL2B_REQUIRE(d && out, "null argument");
+    EXL2B_REQUIRE(d->gate && d->up && d->down, "gate/up/down handles are required");
+    const QMatrix *g = (const QMatrix*)d->gate, *u = (const QMatrix*)d->up, *dn = (const QMatrix*)d->down;
+    EXL2B_REQUIRE(g->v.K == d->hidden_size && u->v.K == d->hidden_size && dn->v.N == d->hidden_size, "mlp matrices have wrong shape");
+    EXL2B_REQUIRE(g->v.N == d->intermediate_size && u->v.N == d->intermediate_size && dn->v.K == d->intermediate_size,
+                  "mlp intermediate size mismatch");
+    EXL2B_REQUIRE(g->device == u->device && g->device == dn->device, "handles on different devices");
+    QMlp* m = new QMlp{*d, g->device};
+    *out = (exl2b_qmlp_t)m;
+    return 0;
+}
+
+extern "C" int exl2b_qmlp_destroy(exl2b_qmlp_t h) {
+    delete (QMlp*)h;
+    return 0;
+}
+
+extern "C" int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b,
+                                  exl2b_stream_t stream_) {
+    (void)temp_b;    // the up projection never materialises: silu(gate)*up is formed in the GEMV epilogue
+    QMlp* m = (QMlp*)h;
+    EXL2B_REQUIRE(m && x && temp_a, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EXL2B_CUDA(cudaSetDevice(m->device));
+    const exl2b_qmlp_desc& d = m->d;
+    const QMatrix *g = (const QMatrix*)d.gate, *u = (const QMatrix*)d.up, *dn = (const QMatrix*)d.down;
+    GemvMat gu[2] = {
+        make_mat(g, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
+        make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
+    };
+    int rc = gemv_launch(m->device, stream, gu, 2, rows, (const half*)d.layernorm, d.norm_epsilon,
+                         d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL);
+    if (rc) return rc;
+    GemvMat down = make_mat(dn, (const half*)temp_a, d.intermediate_size, (half*)x, d.hidden_size, d.has_residual ? 0 : 1);
+    return gemv_launch(m->device, stream, &down, 1, rows, nullptr, 0.f, EPI_STORE);
+}

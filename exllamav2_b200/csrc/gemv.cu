@@ -1,0 +1,538 @@
+// Streaming dequant-GEMV for 1..8 tokens per pass: the B200-native replacement of gemm_half_q_half_kernel
+// (exllamav2_ext/cuda/q_gemm_kernel.cuh:140-565) and gemm_half_q_half_gptq_kernel (q_gemm_kernel_gptq.cuh:61-246).
+//
+// Design:
+//   * stream-K: the launch's unit space (matrix, strip, slab) is cut into gridDim.x equal contiguous ranges, so
+//     every CTA streams the same number of bytes whatever the matrix shape; a range is 1..n "segments", each a
+//     contiguous byte range of ONE strip's stream.
+//   * inside a CTA each of the 8 warps owns a contiguous sub-range of the segment and is its own producer and
+//     consumer: lane 0 issues cp.async.bulk (TMA 1-D) copies of whole slabs into the warp's private 3-stage
+//     shared-memory ring, completion on per-stage mbarriers; no CTA-wide barrier in the main loop.
+//   * the first ring fill is issued BEFORE griddepcontrol.wait: with programmatic dependent launch the weights
+//     of this GEMV are already in flight while the previous kernel (which produces our activations) drains.
+//   * activations are gathered through q_perm (optionally with the RMSNorm folded in) into shared memory once
+//     per segment; weights are unpacked in the fp16 domain straight into mma.m16n8k16 A fragments, tokens are
+//     the N=8 dimension, accumulation is fp32 in registers, group scales are applied per group in fp32.
+//   * split-K partial sums go through a small fp32 workspace; the LAST CTA to arrive for a strip reduces them in
+//     a fixed order (deterministic, no fp16 atomics -- the reference's atomicAdd(half2), q_gemm_kernel.cuh:560,
+//     is not bit-reproducible) and applies the epilogue (bias / residual add / silu(gate)*up).
+#include <algorithm>
+#include <mutex>
+
+#include "dequant.cuh"
+#include "gemv.cuh"
+
+namespace exl2b {
+
+constexpr int GEMV_WARPS = 8;
+constexpr int GEMV_THREADS = GEMV_WARPS * 32;
+constexpr int STAGE_BYTES = 4096;
+constexpr int STAGES = 3;
+constexpr int RING_BYTES = STAGE_BYTES * STAGES;          // per warp
+constexpr int RED_FLOATS = GEMV_MTOK * STRIP_N;           // 512 floats = 2 KB per warp, aliases the ring
+constexpr int SMEM_RINGS = GEMV_WARPS * RING_BYTES;       // 96 KB
+constexpr int SMEM_BARS = GEMV_WARPS * STAGES * 8;
+constexpr int SMEM_MISC = 64;                              // rstd[8] + flags
+
+__host__ __device__ __forceinline__ int run_max(int bits) { return STAGE_BYTES / slab_bytes(bits); }
+
+__device__ __forceinline__ int cta_of_unit(long long x, long long G, long long U) { return (int)(((x + 1) * G - 1) / U); }
+
+// ---- per-slab math ---------------------------------------------------------------------------------------------
+
+template <int BITS>
+__device__ __forceinline__ void load_lane_words(uint32_t base, int lane, uint32_t* mw, uint32_t* ew) {
+    constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
+    if constexpr (Pm == 8) {
+        uint4 a = lds128(base + lane * 16), b = lds128(base + 512 + lane * 16);
+        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
+    } else if constexpr (Pm == 4) {
+        uint4 a = lds128(base + lane * 16);
+        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w;
+    } else {
+        uint2 a = lds64(base + lane * 8);
+        mw[0] = a.x; mw[1] = a.y;
+    }
+    if constexpr (Pe == 1) {
+        ew[0] = lds32(base + 128 * Pm + lane * 4);
+    } else if constexpr (Pe == 2) {
+        uint2 a = lds64(base + 128 * Pm + lane * 8);
+        ew[0] = a.x; ew[1] = a.y;
+    }
+}
+
+// one slab (2 blocks) of an EXL2 strip: acc[blk][sub] += W(16x32 tile)^T-fragments * B
+template <int BITS>
+__device__ __forceinline__ void slab_exl2(uint32_t sm, int lane, const uint32_t (&B)[4], float (&acc)[2][2][4]) {
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        uint32_t mw[8], ew[2], A[16];
+        load_lane_words<BITS>(sm + blk * block_bytes(BITS), lane, mw, ew);
+        dequant_block_exl2<BITS>(mw, ew, A);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) mma16816(acc[blk][sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
+    }
+}
+
+__device__ __forceinline__ void slab_gptq(uint32_t sm, int lane, const uint32_t (&B)[4], const uint32_t (&zc)[2][4],
+                                          float (&acc)[2][2][4]) {
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        uint32_t mw[8], ew[2], A[16];
+        load_lane_words<4>(sm + blk * block_bytes(4), lane, mw, ew);
+        dequant_block_gptq(mw, zc[blk], A);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) mma16816(acc[blk][sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
+    }
+}
+
+// ---- activation functions (reference arithmetic, cuda/q_mlp_activation.cuh:13-52) -------------------------------
+__device__ __forceinline__ half silu_h(half x) {
+    half e = hexp(__hneg(x));
+    half r = hrcp(__hadd(__float2half(1.0f), e));
+    return __hmul(x, r);
+}
+__device__ __forceinline__ half gelu_h(half x) {
+    float xf = __half2float(x);
+    const float c = 0.797884560803f;
+    float t = c * (xf + 0.044715f * xf * xf * xf);
+    // tanh_opt of the reference (cuda/q_mlp_activation.cuh:4-11): tanh.approx on sm_75+
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+    xf = 0.5f * xf * (1.0 + th);
+    return __float2half_rn(xf);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_constant__ GemvParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    griddep_launch_dependents();   // let the next kernel in the stream start prefetching its weights
+
+    const uint32_t smem0 = smem_addr(smem);
+    const uint32_t ring = smem0 + warp * RING_BYTES;
+    const uint32_t bars = smem0 + SMEM_RINGS + warp * STAGES * 8;
+    float* rstd_s = reinterpret_cast<float*>(smem + SMEM_RINGS + SMEM_BARS);
+    int* flag_s = reinterpret_cast<int*>(smem + SMEM_RINGS + SMEM_BARS + 32);
+    uint8_t* act_s = smem + SMEM_RINGS + SMEM_BARS + SMEM_MISC;
+    const uint32_t act0 = smem0 + SMEM_RINGS + SMEM_BARS + SMEM_MISC;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    }
+    mbar_fence_init();
+    __syncwarp();
+
+    const long long U = P.total_units, G = gridDim.x;
+    const int u0 = (int)((long long)blockIdx.x * U / G), u1 = (int)((long long)(blockIdx.x + 1) * U / G);
+    const int KS = P.KS, M = P.M;
+
+    uint32_t phases = 0;          // parity bit per stage
+    bool first_seg = true;
+    int u = u0;
+    while (u < u1) {
+        int mi = 0;
+        while (mi + 1 < P.num_mats && u >= P.mat[mi + 1].unit_begin) ++mi;
+        const GemvMat& mt = P.mat[mi];
+        const QMatView& w = mt.w;
+        const int local = u - mt.unit_begin;
+        const int strip = local / KS, ks0 = local - strip * KS;
+        const int seg = min(KS - ks0, u1 - u);
+        const int wk0 = ks0 + (seg * warp) / GEMV_WARPS, wk1 = ks0 + (seg * (warp + 1)) / GEMV_WARPS;
+        const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes;
+
+        // ---- producer: fill the ring (weights never depend on a previous kernel) ----
+        int fetch_ks = wk0, fstage = 0, cstage = 0;
+        auto issue = [&]() {
+            const uint2 tab = __ldg(w.slab_tab + fetch_ks);
+            const int bits = (tab.y >> 16) & 0xF;
+            const int run = min(min(run_max(bits), (int)(tab.y >> 20)), wk1 - fetch_ks);
+            const uint32_t bytes = (uint32_t)run * slab_bytes(bits);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
+                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + tab.x, bytes, bars + 8 * fstage);
+            }
+            fetch_ks += run;
+            fstage = (fstage + 1 == STAGES) ? 0 : fstage + 1;
+        };
+#pragma unroll 1
+        for (int s = 0; s < STAGES && fetch_ks < wk1; ++s) issue();
+
+        if (first_seg) griddep_wait();   // from here on we may read what the previous kernel wrote
+
+        // ---- stage activations a'[m][r] = f(x[m][perm[k0+r]]) for the segment's rows ----
+        if (first_seg && P.norm_w) {
+            // RMSNorm statistics per token (cuda/rms_norm.cu:55-111): clamp, fp32 sum of squares, rsqrt(mean+eps)
+            const int K = w.K;
+            for (int m = warp; m < M; m += GEMV_WARPS) {
+                const half* xr = mt.x + (size_t)m * mt.ldx;
+                float sum = 0.f;
+                for (int k = lane * 2; k < K; k += 64) {
+                    const half2 x2 = *reinterpret_cast<const half2*>(xr + k);
+                    float f0 = fmaxf(-65504.f, fminf(__low2float(x2), 65504.f));
+                    float f1 = fmaxf(-65504.f, fminf(__high2float(x2), 65504.f));
+                    sum = fmaf(f0, f0, sum);
+                    sum = fmaf(f1, f1, sum);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
+            }
+            __syncthreads();
+        }
+        {
+            const int rows = seg * SLAB_K, k0 = ks0 * SLAB_K;
+            for (int idx = tid; idx < rows * M; idx += GEMV_THREADS) {
+                const int m = idx / rows, r = idx - m * rows;
+                const int kp = k0 + r;
+                const int src = w.perm ? (int)__ldg(w.perm + kp) : kp;
+                half v = mt.x[(size_t)m * mt.ldx + src];
+                if (P.norm_w) {
+                    float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
+                    v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
+                }
+                *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
+            }
+        }
+        first_seg = false;
+        __syncthreads();
+
+        // ---- consumer ----
+        float acc_tot[2][2][4], acc_g[2][2][4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc_tot[a][b][c] = 0.f, acc_g[a][b][c] = 0.f;
+
+        int cur_group = -1;
+        uint32_t sw[8];              // EXL2: 8 scale words of (group, strip); GPTQ: zero words
+        half gsc[8];                 // GPTQ: fp16 scales of the lane's 8 columns
+        half smax = __float2half(0.f);
+        uint32_t zc[2][4];
+        const int n_words = w.N >> 3;
+
+        auto flush = [&]() {         // acc_tot += scale(group, n) * acc_g ; acc_g = 0
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int j = 4 * blk + 2 * sub + rr;
+                        float s;
+                        if (!w.is_gptq) {
+                            const int q = (int)((sw[j] >> (4 * g)) & 15u) + 1;
+                            s = __half2float(__hmul(__int2half_rn(q * q), smax));   // fp16 scale, qdq_util.cuh:24-30
+                        } else {
+                            s = __half2float(gsc[j]);
+                        }
+                        acc_tot[blk][sub][2 * rr + 0] = fmaf(s, acc_g[blk][sub][2 * rr + 0], acc_tot[blk][sub][2 * rr + 0]);
+                        acc_tot[blk][sub][2 * rr + 1] = fmaf(s, acc_g[blk][sub][2 * rr + 1], acc_tot[blk][sub][2 * rr + 1]);
+                        acc_g[blk][sub][2 * rr + 0] = 0.f;
+                        acc_g[blk][sub][2 * rr + 1] = 0.f;
+                    }
+        };
+        auto enter_group = [&](int grp) {
+            cur_group = grp;
+            const uint32_t* src = (w.is_gptq ? w.qzeros : w.q_scale) + (size_t)grp * n_words + strip * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sw[j] = (strip * 8 + j < n_words) ? __ldg(src + j) : 0u;
+            if (!w.is_gptq) {
+                smax = w.q_scale_max[grp];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = strip * STRIP_N + (j >> 2) * 32 + ((j >> 1) & 1) * 16 + (j & 1) * 8 + g;
+                    gsc[j] = (n < w.N) ? w.gptq_scales[(size_t)grp * w.N + n] : __float2half(0.f);
+                    const int z1 = (int)((sw[j] >> (4 * g)) & 15u) + 1;      // zero + 1, q_gemm_kernel_gptq.cuh:169
+                    const half2 c2 = __half2half2(__int2half_rn(-(((j & 1) ? 64 : 1024) + z1)));
+                    zc[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&c2);
+                }
+            }
+        };
+
+        int cons_ks = wk0;
+        while (cons_ks < wk1) {
+            const uint2 tab = __ldg(w.slab_tab + cons_ks);
+            const int bits = (tab.y >> 16) & 0xF;
+            const int run = min(min(run_max(bits), (int)(tab.y >> 20)), wk1 - cons_ks);
+            mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
+            phases ^= 1u << cstage;
+            const uint32_t sbase = ring + cstage * STAGE_BYTES;
+#pragma unroll 1
+            for (int i = 0; i < run; ++i) {
+                const int ks = cons_ks + i;
+                const int grp = (int)(__ldg(&w.slab_tab[ks].y) & 0xFFFFu);
+                if (grp != cur_group) {
+                    if (cur_group >= 0) flush();
+                    enter_group(grp);
+                }
+                uint32_t B[4] = {0u, 0u, 0u, 0u};
+                if (g < M) {
+                    const uint4 b4 = lds128(act0 + g * P.act_stride + (ks - ks0) * (SLAB_K * 2) + t * 16);
+                    B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w;
+                }
+                const uint32_t sm = sbase + i * slab_bytes(bits);
+                if (w.is_gptq) {
+                    slab_gptq(sm, lane, B, zc, acc_g);
+                } else {
+                    switch (bits) {
+                        case 4: slab_exl2<4>(sm, lane, B, acc_g); break;
+                        case 5: slab_exl2<5>(sm, lane, B, acc_g); break;
+                        case 3: slab_exl2<3>(sm, lane, B, acc_g); break;
+                        case 6: slab_exl2<6>(sm, lane, B, acc_g); break;
+                        case 2: slab_exl2<2>(sm, lane, B, acc_g); break;
+                        default: slab_exl2<8>(sm, lane, B, acc_g); break;
+                    }
+                }
+            }
+            __syncwarp();
+            cons_ks += run;
+            cstage = (cstage + 1 == STAGES) ? 0 : cstage + 1;
+            if (fetch_ks < wk1) issue();     // refill the stage we just drained
+        }
+        if (cur_group >= 0) flush();
+
+        // ---- cross-warp reduction (the ring memory is idle now) ----
+        __syncthreads();
+        {
+            float* red = reinterpret_cast<float*>(smem + warp * RING_BYTES);
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int tok = 2 * t + e;
+                            if (tok < M) red[tok * STRIP_N + 32 * blk + 16 * sub + 8 * rr + g] = acc_tot[blk][sub][2 * rr + e];
+                        }
+        }
+        __syncthreads();
+
+        const int gs = mt.strip_begin + strip;
+        const long long sb = (long long)mt.unit_begin + (long long)strip * KS;
+        const int first_cta = cta_of_unit(sb, G, U), last_cta = cta_of_unit(sb + KS - 1, G, U);
+        const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
+        const bool paired = P.epilogue != EPI_STORE;
+        const int n_out = M * STRIP_N;
+
+        auto epilogue_store = [&](int o, float v) {
+            const int tok = o >> 6, n = strip * STRIP_N + (o & 63);
+            if (n < w.N) {
+                if (w.bias) v += __half2float(w.bias[n]);
+                half* cp = mt.c + (size_t)tok * mt.ldc + n;
+                if (!mt.clear) v += __half2float(*cp);
+                *cp = __float2half_rn(v);
+            }
+        };
+
+        if (nc == 1 && !paired) {
+            for (int o = tid; o < n_out; o += GEMV_THREADS) {
+                float v = 0.f;
+#pragma unroll
+                for (int wi = 0; wi < GEMV_WARPS; ++wi) v += reinterpret_cast<const float*>(smem + wi * RING_BYTES)[o];
+                epilogue_store(o, v);
+            }
+        } else {
+            float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * RED_FLOATS;
+            for (int o = tid; o < n_out; o += GEMV_THREADS) {
+                float v = 0.f;
+#pragma unroll
+                for (int wi = 0; wi < GEMV_WARPS; ++wi) v += reinterpret_cast<const float*>(smem + wi * RING_BYTES)[o];
+                __stcg(wsp + o, v);
+            }
+            __threadfence();
+            __syncthreads();
+            int expected = nc, cidx = gs;
+            if (paired) {
+                // gate strip j and up strip j share one counter (the gate's) and are finalised together
+                const GemvMat& other = P.mat[1 - mi];
+                const long long ob = (long long)other.unit_begin + (long long)strip * KS;
+                expected += cta_of_unit(ob + KS - 1, G, U) - cta_of_unit(ob, G, U) + 1;
+                cidx = P.mat[0].strip_begin + strip;
+            }
+            if (tid == 0) {
+                const unsigned int old = atomicAdd(P.counters + cidx, 1u);
+                *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (*flag_s) {
+                __threadfence();
+                if (!paired) {
+                    const float* base = P.ws + (size_t)gs * P.maxc * RED_FLOATS;
+                    for (int o = tid; o < n_out; o += GEMV_THREADS) {
+                        float v = 0.f;
+                        for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * RED_FLOATS + o);
+                        epilogue_store(o, v);
+                    }
+                } else {
+                    const GemvMat& mg = P.mat[0];
+                    const GemvMat& mu = P.mat[1];
+                    const long long gb = (long long)mg.unit_begin + (long long)strip * KS;
+                    const long long ub = (long long)mu.unit_begin + (long long)strip * KS;
+                    const int ncg = cta_of_unit(gb + KS - 1, G, U) - cta_of_unit(gb, G, U) + 1;
+                    const int ncu = cta_of_unit(ub + KS - 1, G, U) - cta_of_unit(ub, G, U) + 1;
+                    const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * RED_FLOATS;
+                    const float* bu = P.ws + (size_t)(mu.strip_begin + strip) * P.maxc * RED_FLOATS;
+                    for (int o = tid; o < n_out; o += GEMV_THREADS) {
+                        float vg = 0.f, vu = 0.f;
+                        for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * RED_FLOATS + o);
+                        for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * RED_FLOATS + o);
+                        const int tok = o >> 6, n = strip * STRIP_N + (o & 63);
+                        if (n < mg.w.N) {
+                            if (mg.w.bias) vg += __half2float(mg.w.bias[n]);
+                            if (mu.w.bias) vu += __half2float(mu.w.bias[n]);
+                            // the reference rounds gate and up to fp16 (temp_a / temp_b) before act_mul (q_mlp.cu:187-196)
+                            const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);
+                            const half a = (P.epilogue == EPI_GELU_MUL) ? gelu_h(hg) : silu_h(hg);
+                            mg.c[(size_t)tok * mg.ldc + n] = __hmul(a, hu);
+                        }
+                    }
+                }
+                if (tid == 0) P.counters[cidx] = 0u;     // ready for the next launch (stream-ordered)
+            }
+        }
+        __syncthreads();      // ring / act memory is reused by the next segment
+        u += seg;
+    }
+}
+
+// ---- host launcher -----------------------------------------------------------------------------------------------
+
+struct DeviceWorkspace {
+    float* ws = nullptr;
+    unsigned int* counters = nullptr;
+    size_t ws_bytes = 0;
+    int n_counters = 0;
+    bool attr_set = false;
+};
+static DeviceWorkspace g_ws[64];
+static std::mutex g_ws_mutex;
+
+static int ensure_workspace(int device, DeviceWorkspace** out) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    DeviceWorkspace& d = g_ws[device];
+    if (!d.ws) {
+        d.ws_bytes = (size_t)64 << 20;
+        d.n_counters = 1 << 20;
+        EXL2B_CUDA(cudaMalloc(&d.ws, d.ws_bytes));
+        EXL2B_CUDA(cudaMalloc(&d.counters, d.n_counters * sizeof(unsigned int)));
+        EXL2B_CUDA(cudaMemset(d.counters, 0, d.n_counters * sizeof(unsigned int)));
+        EXL2B_CUDA(cudaDeviceSynchronize());
+    }
+    if (!d.attr_set) {
+        EXL2B_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        d.attr_set = true;
+    }
+    *out = &d;
+    return 0;
+}
+
+int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps,
+                int epilogue) {
+    EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
+    EXL2B_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
+    if (M <= 0) return 0;
+    DeviceWorkspace* dw = nullptr;
+    int rc = ensure_workspace(device, &dw);
+    if (rc) return rc;
+
+    GemvParams P = {};
+    P.num_mats = nm;
+    P.KS = mats[0].w.KS;
+    int units = 0, strips = 0;
+    for (int i = 0; i < nm; ++i) {
+        EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
+        P.mat[i] = mats[i];
+        P.mat[i].unit_begin = units;
+        P.mat[i].strip_begin = strips;
+        units += mats[i].w.strips * P.KS;
+        strips += mats[i].w.strips;
+    }
+    if (epilogue != EPI_STORE)
+        EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
+    P.total_units = units;
+    P.norm_w = norm_w;
+    P.norm_eps = norm_eps;
+    P.epilogue = epilogue;
+    P.ws = dw->ws;
+    P.counters = dw->counters;
+
+    const int sms = device_sm_count(device);
+    const int grid = std::max(1, std::min(2 * sms, units));
+    const int seg_max = std::min(P.KS, (units + grid - 1) / grid);
+    P.act_rows = seg_max * SLAB_K;
+    P.act_stride = ((P.act_rows * 2 + 127) / 128) * 128 + 64;
+    P.maxc = (int)(((long long)P.KS * grid) / units) + 2;
+    EXL2B_REQUIRE(strips <= dw->n_counters, "too many strips for the counter array");
+    EXL2B_REQUIRE((size_t)strips * P.maxc * RED_FLOATS * sizeof(float) <= dw->ws_bytes, "split-K workspace too small");
+
+    const int fixed = SMEM_RINGS + SMEM_BARS + SMEM_MISC;
+    int tok_per_pass = std::min(GEMV_MTOK, (227 * 1024 - fixed) / P.act_stride);
+    EXL2B_REQUIRE(tok_per_pass >= 1, "K too large to stage one activation row (%d bytes)", P.act_stride);
+
+    for (int m0 = 0; m0 < M; m0 += tok_per_pass) {
+        P.M = std::min(tok_per_pass, M - m0);
+        for (int i = 0; i < nm; ++i) {
+            P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
+            P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
+        }
+        const size_t smem = (size_t)fixed + (size_t)P.M * P.act_stride;
+        EXL2B_CUDA(launch_pdl(gemv_kernel, dim3(grid), dim3(GEMV_THREADS), smem, stream, P));
+    }
+    return 0;
+}
+
+}  // namespace exl2b
+
+using namespace exl2b;
+
+extern "C" int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int lda, uint16_t* c, int ldc, int m,
+                                      int clear, int force_cuda, exl2b_stream_t stream) {
+    (void)force_cuda;
+    QMatrix* q = (QMatrix*)h;
+    EXL2B_REQUIRE(q && a && c, "null argument");
+    EXL2B_REQUIRE(lda >= q->v.K && ldc >= q->v.N, "leading dimensions too small");
+    EXL2B_CUDA(cudaSetDevice(q->device));
+    GemvMat mt = {};
+    mt.w = q->v;
+    mt.x = (const half*)a;
+    mt.ldx = lda;
+    mt.c = (half*)c;
+    mt.ldc = ldc;
+    mt.clear = clear ? 1 : 0;
+    return gemv_launch(q->device, (cudaStream_t)stream, &mt, 1, m, nullptr, 0.f, EPI_STORE);
+}
+
+extern "C" int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_host, uint16_t* c_host, int m,
+                                           exl2b_stream_t stream_) {
+    QMatrix* q = (QMatrix*)h;
+    EXL2B_REQUIRE(q && a_host && c_host && m > 0, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EXL2B_CUDA(cudaSetDevice(q->device));
+    const size_t ab = (size_t)m * q->v.K * 2, cb = (size_t)m * q->v.N * 2;
+    uint16_t *da = nullptr, *dc = nullptr;
+    EXL2B_CUDA(cudaMallocAsync(&da, ab, stream));
+    EXL2B_CUDA(cudaMallocAsync(&dc, cb, stream));
+    EXL2B_CUDA(cudaMemcpyAsync(da, a_host, ab, cudaMemcpyHostToDevice, stream));
+    int rc = exl2b_gemm_half_q_half(h, da, q->v.K, dc, q->v.N, m, 1, 0, stream_);
+    if (rc == 0) {
+        EXL2B_CUDA(cudaMemcpyAsync(c_host, dc, cb, cudaMemcpyDeviceToHost, stream));
+    }
+    cudaFreeAsync(da, stream);
+    cudaFreeAsync(dc, stream);
+    EXL2B_CUDA(cudaStreamSynchronize(stream));
+    return rc;
+}

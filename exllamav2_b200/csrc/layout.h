@@ -1,0 +1,144 @@
+// Private HBM layout of a quantized matrix and the register-level unpack -- shared by the repack kernel, the
+// GEMV / GEMM kernels, reconstruct, and the host-side emulation in tests/emu (compiled with g++).
+//
+// The reference keeps the checkpoint's [packed-row, column] order and re-shuffles bit fields inside each
+// 32-row column unit at load time (exllamav2_ext/cuda/q_matrix.cu:21-44, quant/qdq_*.cuh shuffle_*).  We do a
+// different load-time re-pack (same total bytes, written back over q_weight exactly like the reference mutates
+// it) into a layout built for B200 streaming:
+//
+//   strip  = 64 output columns; a strip's data is ONE contiguous byte stream over K, so any (strip, k-range)
+//            is a contiguous range that a warp fetches with cp.async.bulk (TMA 1-D) into shared memory.
+//   slab   = 32 consecutive stored rows k' of one strip = 2 blocks.
+//   block  = 32 k x 32 n.  Lane l (g = l>>2, t = l&3) owns 32 values: n in {g, g+8, g+16, g+24},
+//            k in {8t..8t+7}, stored so that after unpacking, registers ARE mma.m16n8k16 A-fragments
+//            (weights = A operand, tokens = the N=8 dimension).
+//   plane  = a b-bit value is split into power-of-two bit planes (b = main + extra: 2=2, 3=2+1, 4=4, 5=4+1,
+//            6=4+2, 8=8) so that every field sits at a position where `(w >> sh) & mask | magic` is a valid
+//            fp16 (the 0x6400 trick generalised to every exponent), two values per 32-bit op.
+//
+// Value index inside a lane's 32 values:  i = p*2 + e,  pair p = sub*8 + s*4 + reg,  reg = h*2 + rr
+//   n_local = sub*16 + rr*8 + g          (sub: 16-column subtile, rr: row g / g+8 of the mma tile)
+//   k_local = 8t + 4s + 2h + e           (s: mma k-step, h: column half, e: element of the half2)
+// mma A registers of (sub, s):  A[reg] = half2(value e=0, value e=1).  The matching B fragment of step s is
+//   B0 = act[8t+4s+{0,1}],  B1 = act[8t+4s+{2,3}]  -> one 16-byte load of act[8t..8t+7] feeds both steps.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EXL2B_HD __host__ __device__ __forceinline__
+#else
+#define EXL2B_HD inline
+#endif
+
+namespace exl2b {
+
+constexpr int SLAB_K = 32;
+constexpr int BLOCK_N = 32;
+constexpr int STRIP_BLOCKS = 2;
+constexpr int STRIP_N = BLOCK_N * STRIP_BLOCKS;   // 64
+
+EXL2B_HD constexpr int plane_main(int bits) { return bits == 2 ? 2 : bits == 3 ? 2 : bits == 8 ? 8 : 4; }
+EXL2B_HD constexpr int plane_extra(int bits) { return bits == 3 ? 1 : bits == 5 ? 1 : bits == 6 ? 2 : 0; }
+EXL2B_HD constexpr bool bits_supported(int b) { return b == 2 || b == 3 || b == 4 || b == 5 || b == 6 || b == 8; }
+
+// bytes of one block / one slab at a bit width (== the checkpoint's bytes for the same values)
+EXL2B_HD constexpr int block_bytes(int bits) { return 128 * bits; }
+EXL2B_HD constexpr int slab_bytes(int bits) { return block_bytes(bits) * STRIP_BLOCKS; }
+
+// A plane with P bits per field stores P words per lane (32 values * P bits).  Segment = lane-major array of
+// up to 4 words per lane (so a lane's words are one aligned 4/8/16-byte shared-memory load); the 8-bit plane is
+// two 4-word segments.  Word offsets (in uint32) of a segment inside a block:
+EXL2B_HD constexpr int main_words(int bits) { return plane_main(bits); }          // words per lane
+EXL2B_HD constexpr int extra_words(int bits) { return plane_extra(bits); }
+// main plane: P<=4: one segment at word 0 with P words/lane. P==8: segment A (pairs 0..7) at 0, B at 128.
+EXL2B_HD constexpr int main_seg_words(int bits) { return plane_main(bits) == 8 ? 4 : plane_main(bits); }
+EXL2B_HD constexpr int extra_seg_base(int bits) { return 32 * plane_main(bits); }   // in words, from block start
+
+// pair slot p (0..15) of a plane with P bits: which word of the lane, and field slot j inside the word
+EXL2B_HD constexpr int pairs_per_word(int P) { return 16 / P; }
+EXL2B_HD constexpr int pair_word(int P, int p) { return p / pairs_per_word(P); }
+EXL2B_HD constexpr int pair_slot(int P, int p) { return p % pairs_per_word(P); }
+// field e of pair slot j sits at bit  16*e + P*j  of its word
+EXL2B_HD constexpr int field_bit(int P, int j, int e) { return 16 * e + P * j; }
+// extraction: shift the word right by sh, then the field is at in-halfword offset off (off + P <= 10)
+EXL2B_HD constexpr int field_sh(int P, int j) { return (P * j + P <= 10) ? 0 : ((P == 4 || P == 8) ? 8 : 10); }
+EXL2B_HD constexpr int field_off(int P, int j) { return P * j - field_sh(P, j); }
+EXL2B_HD constexpr uint32_t field_mask(int P, int j) {
+    return (uint32_t)(((1u << P) - 1u) << field_off(P, j)) * 0x00010001u;
+}
+// fp16 magic: exponent E = 10 - off so that  bits(mask&w | magic)  ==  2^E + field   exactly
+EXL2B_HD constexpr int field_exp(int P, int j) { return 10 - field_off(P, j); }
+EXL2B_HD constexpr uint32_t field_magic(int P, int j) { return (uint32_t)((field_exp(P, j) + 15) << 10) * 0x00010001u; }
+
+// fp16 bit pattern of a (possibly negative) integer-valued constant that is exactly representable
+EXL2B_HD constexpr uint16_t f16_bits_of_int(int v) {
+    // v = +-m * 2^k with m < 2048
+    if (v == 0) return 0;
+    uint16_t sign = v < 0 ? 0x8000 : 0;
+    uint32_t a = (uint32_t)(v < 0 ? -v : v);
+    int e = 0;
+    while ((a >> e) >= 2048u) e++;          // drop low zero bits (caller guarantees exactness)
+    uint32_t m = a >> e;
+    int top = 0;
+    while ((m >> (top + 1)) != 0) top++;    // position of leading one
+    int exp = top + e;                      // value = 1.xxx * 2^exp
+    uint32_t frac = ((m << (10 - top)) & 0x3FFu);
+    return (uint16_t)(sign | ((uint32_t)(exp + 15) << 10) | frac);
+}
+EXL2B_HD constexpr uint32_t h2_const_int(int v) { return (uint32_t)f16_bits_of_int(v) * 0x00010001u; }
+
+// --------------------------------------------------------------------------------------------------------------
+// where a value lives (used by the repack kernel and the host emulation)
+// --------------------------------------------------------------------------------------------------------------
+struct ValuePos { int n_local; int k_local; };
+EXL2B_HD constexpr ValuePos value_pos(int lane, int i) {
+    int g = lane >> 2, t = lane & 3;
+    int e = i & 1, p = i >> 1;
+    int rr = p & 1, h = (p >> 1) & 1, s = (p >> 2) & 1, sub = (p >> 3) & 1;
+    return ValuePos{sub * 16 + rr * 8 + g, 8 * t + 4 * s + 2 * h + e};
+}
+// inverse: which (lane, i) holds (n_local, k_local)
+EXL2B_HD constexpr int lane_of(int n_local, int k_local) { return ((n_local & 7) << 2) | (k_local >> 3); }
+EXL2B_HD constexpr int index_of(int n_local, int k_local) {
+    int sub = n_local >> 4, rr = (n_local >> 3) & 1;
+    int kk = k_local & 7;
+    int s = kk >> 2, h = (kk >> 1) & 1, e = kk & 1;
+    int p = sub * 8 + s * 4 + h * 2 + rr;
+    return p * 2 + e;
+}
+
+// Compose the lane's plane words from its 32 integer values q[i] (0 <= q < 2^bits).
+// out_main: main_words(bits) words, out_extra: extra_words(bits) words.
+EXL2B_HD void compose_lane_words(int bits, const uint32_t* q, uint32_t* out_main, uint32_t* out_extra) {
+    const int Pm = plane_main(bits), Pe = plane_extra(bits);
+    for (int w = 0; w < Pm; ++w) out_main[w] = 0u;
+    for (int w = 0; w < Pe; ++w) out_extra[w] = 0u;
+    for (int i = 0; i < 32; ++i) {
+        int p = i >> 1, e = i & 1;
+        uint32_t fm = q[i] & ((1u << Pm) - 1u);
+        out_main[pair_word(Pm, p)] |= fm << field_bit(Pm, pair_slot(Pm, p), e);
+        if (Pe) {
+            uint32_t fe = (q[i] >> Pm) & ((1u << Pe) - 1u);
+            out_extra[pair_word(Pe, p)] |= fe << field_bit(Pe, pair_slot(Pe, p), e);
+        }
+    }
+}
+
+// word offset (uint32 units, from the block start) of word `w` of lane `lane` in the main / extra plane
+EXL2B_HD constexpr int main_word_index(int bits, int lane, int w) {
+    return plane_main(bits) == 8 ? ((w >> 2) * 128 + lane * 4 + (w & 3)) : (lane * plane_main(bits) + w);
+}
+EXL2B_HD constexpr int extra_word_index(int bits, int lane, int w) {
+    return extra_seg_base(bits) + lane * plane_extra(bits) + w;
+}
+
+// Inverse of compose (integer domain; the fp16-domain unpack used by the kernels is in dequant.cuh).
+EXL2B_HD uint32_t extract_value(int bits, const uint32_t* lane_main, const uint32_t* lane_extra, int i) {
+    const int Pm = plane_main(bits), Pe = plane_extra(bits);
+    int p = i >> 1, e = i & 1;
+    uint32_t v = (lane_main[pair_word(Pm, p)] >> field_bit(Pm, pair_slot(Pm, p), e)) & ((1u << Pm) - 1u);
+    if (Pe) v |= ((lane_extra[pair_word(Pe, p)] >> field_bit(Pe, pair_slot(Pe, p), e)) & ((1u << Pe) - 1u)) << Pm;
+    return v;
+}
+
+}  // namespace exl2b

@@ -1,0 +1,39 @@
+// Internal QMatrix handle (the reference's class QMatrix, exllamav2_ext/cuda/q_matrix.cuh:11-83).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace exl2b {
+
+// Device-side view handed to kernels by value.
+struct QMatView {
+    const uint32_t* packed;       // [strips][strip_bytes]  private layout
+    const uint2* slab_tab;        // [KS]  .x = byte offset of the slab inside a strip,
+                                  //       .y = group | bits << 16 | slabs-left-with-same-bits << 20
+    const uint32_t* q_scale;      // EXL2 int32[G, N/8]   (checkpoint layout, read directly)
+    const half* q_scale_max;      // EXL2 fp16[G]
+    const uint32_t* qzeros;       // GPTQ int32[G, N/8]
+    const half* gptq_scales;      // GPTQ fp16[G, N]
+    const uint16_t* perm;         // [K] or NULL
+    const half* bias;             // [N] or NULL
+    uint32_t strip_bytes;
+    int K, N, KS, strips, groups;
+    int is_gptq;
+};
+
+struct QMatrix {
+    int device = 0;
+    QMatView v = {};
+    uint32_t* owned_packed = nullptr;   // only when width % 64 != 0 (padded copy); otherwise packed aliases q_weight
+    void* tables = nullptr;             // slab_tab storage
+    uint32_t bits_mask = 0;             // bit b set <=> some group uses b bits
+    uint64_t packed_bytes = 0;
+    std::vector<uint2> slab_tab_host;
+};
+
+inline uint32_t meta_group(uint32_t m) { return m & 0xFFFFu; }
+inline uint32_t meta_bits(uint32_t m) { return (m >> 16) & 0xFu; }
+inline uint32_t meta_left(uint32_t m) { return m >> 20; }
+
+}  // namespace exl2b

@@ -1,0 +1,82 @@
+"""Synthetic checkpoints generated directly on the GPU in the reference's on-disk tensor format (EXL2 / GPTQ).
+
+There is no network, hence no real weights: bench.py and the decode model use random-bit tensors of the exact
+shapes/dtypes a converted model has.  A uniformly random bit stream IS a uniformly
+random q for every bit width, so q_weight is just random int32 words; group tables follow
+conversion/qparams.py:73-84 (the converter's group plan).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def group_plan(K: int, bits, bits_prop, group_size) -> list[tuple[int, int]]:
+    if isinstance(group_size, int):
+        group_size = {b: group_size for b in bits}
+    elif isinstance(group_size, (list, tuple)):
+        group_size = {b: g for b, g in zip(bits, group_size)}
+    plan, remaining = [], K
+    for b, p in zip(bits, bits_prop):
+        gsz = group_size[b]
+        g = math.ceil(min(K * p, remaining) / gsz)
+        for _ in range(g):
+            rows = min(gsz, remaining)
+            if rows <= 0:
+                break
+            plan.append((b, rows))
+            remaining -= rows
+    assert remaining <= 0
+    return plan
+
+
+def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, device="cuda:0", seed: int = 0,
+                perm: bool = True) -> dict:
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    plan = group_plan(K, list(bits), list(bits_prop), group_size)
+    G = len(plan)
+    q_groups = torch.zeros((2 * G,), dtype=torch.int16)
+    qrow = 0
+    for gi, (b, rows) in enumerate(plan):
+        q_groups[2 * gi] = b
+        q_groups[2 * gi + 1] = qrow
+        qrow += rows * b // 32
+    w = {
+        "q_weight": torch.randint(-2**31, 2**31 - 1, (qrow, N), dtype=torch.int32, device=device, generator=gen),
+        "q_scale": torch.randint(-2**31, 2**31 - 1, (G, N // 8), dtype=torch.int32, device=device, generator=gen),
+        "q_scale_max": (torch.rand((G,), device=device, generator=gen) * 3.5 + 0.5).half(),
+        "q_groups": q_groups.to(device),
+        "q_invperm": (torch.randperm(K, device=device, generator=gen) if perm else torch.arange(K, device=device)).to(torch.int32),
+    }
+    w["q_perm"] = torch.argsort(w["q_invperm"]).to(torch.int)
+    return w
+
+
+def random_gptq(K: int, N: int, group_size: int = 128, device="cuda:0", seed: int = 0, act_order: bool = False) -> dict:
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    G = K // group_size
+    g_idx = (torch.arange(K) // group_size).to(torch.int32)
+    if act_order:
+        g_idx = g_idx[torch.randperm(K, generator=torch.Generator().manual_seed(seed))]
+    return {
+        "qweight": torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen),
+        "qzeros": torch.randint(-2**31, 2**31 - 1, (G, N // 8), dtype=torch.int32, device=device, generator=gen),
+        "scales": (torch.rand((G, N), device=device, generator=gen) * 0.018 + 0.002).half(),
+        "g_idx": g_idx,
+    }
+
+
+def algorithmic_bytes(w: dict, M: int = 1, accumulate: bool = False) -> int:
+    """Bytes a linear call must move: packed weights + scales (+ u16 perm) + a + c."""
+    if "q_weight" in w:
+        K, N = w["q_invperm"].shape[0], w["q_weight"].shape[1]
+        b = w["q_weight"].numel() * 4 + w["q_scale"].numel() * 4 + w["q_scale_max"].numel() * 2 + 2 * K
+    else:
+        K, N = w["qweight"].shape[0] * 8, w["qweight"].shape[1]
+        b = w["qweight"].numel() * 4 + w["qzeros"].numel() * 4 + w["scales"].numel() * 2
+        if "q_perm" in w:
+            b += 2 * K
+    return b + 2 * M * K + 2 * M * N * (2 if accumulate else 1)
