@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s (bs=1) of a Llama-2-7B-shaped EXL2 ~4.0 bpw model on the B200-native hot path,
+with the q_gemm path's achieved HBM GB/s against the measured roofline.  BASELINE.json metric / configs[2].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model PRESET]
+
+A "step" is one decode token: embedding -> 32 x (Q4-KV unpack, RMSNorm+QKV+RoPE, paged attention, Q4-KV pack,
+O-proj+residual, RMSNorm+gate|up+silu*mul, down+residual) -> RMSNorm -> lm_head.  Weights are synthetic tensors in the
+reference's on-disk EXL2 format (no network), resident in HBM; 3.3 GB of packed weights per token >> 126 MB L2, so no
+L2 flush is needed between steps ("inputs_exceed_l2").
+
+JSON keys (one line on stdout):
+  value / ms_per_step   device-timed (CUDA events) over K graph replays, next token chosen by an on-device argmax
+  e2e                   same metric through the public API with HOST buffers: pinned token id -> H2D, decode,
+                        fp16 logits -> pinned host (D2H), host argmax, every step
+  roofline              the dominant kernel (gemv_kernel): sum of algorithmic bytes of every linear of the model
+                        / device time of exactly those launches replayed back to back, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline          oracle/exl2_cpu.c (the CPU port of the reference's q_gemm) on the host cores, bounded sample
+  --impl reference      the CPU arm alone (the reference has no CPU q_gemm; its CUDA extension is timed separately by
+                        tools/microbench.py --ref and reported under "reference_cuda_ext" when oracle/_ref is present)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode tokens/sec (bs=1) Llama2-7B EXL2-4.0bpw"
+UNIT = "tokens/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------------------------
+
+def measured_peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(s) > col and s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        mx = next((int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_port_baseline(cfg, budget_s: float = 12.0) -> dict:
+    """Time oracle/exl2_cpu.c (fused CPU dequant-GEMV over the checkpoint layout) on ONE decoder layer's seven
+    matrices (1/num_layers of the layer weights), all host threads; extrapolate to tokens/s."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+    from exllamav2_b200 import synthetic
+    lib = oracle_c.load()
+    threads = lib.exl2_cpu_threads()
+    rng = np.random.default_rng(0)
+    hid, inter, H, KVH, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+
+    def rand_exl2(K, N, plan):
+        bits, prop, gs = plan
+        gp = synthetic.group_plan(K, list(bits), list(prop), gs)
+        G = len(gp)
+        qg = np.zeros((2 * G,), dtype=np.int16)
+        row = 0
+        for i, (b, rows) in enumerate(gp):
+            qg[2 * i], qg[2 * i + 1] = b, row
+            row += rows * b // 32
+        return dict(qw=rng.integers(0, 2**32, size=(row, N), dtype=np.uint32), qs=rng.integers(0, 2**32, size=(G, N // 8), dtype=np.uint32),
+                    smax=rng.uniform(0.002, 0.015, size=(G,)).astype(np.float16).view(np.uint16), qg=qg,
+                    perm=rng.permutation(K).astype(np.uint16), K=K, N=N, G=G, R=row)
+
+    mp = cfg.plan.mlp[0]
+    mats = [rand_exl2(hid, H * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn),
+            rand_exl2(H * hd, hid, cfg.plan.attn), rand_exl2(hid, inter, mp), rand_exl2(hid, inter, mp), rand_exl2(inter, hid, mp)]
+    ins = [rng.normal(size=(m["K"],)).astype(np.float32) for m in mats]
+    outs = [np.empty((m["N"],), dtype=np.float32) for m in mats]
+
+    def one_layer():
+        for m, a, y in zip(mats, ins, outs):
+            oracle_c.exl2_gemv_prepared(lib, m, a, y)
+
+    one_layer()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one_layer()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    t_layer = (time.perf_counter() - t0) / n
+    layer_w = sum(m["qw"].nbytes for m in mats)
+    head_w = cfg.hidden_size * cfg.vocab_size * cfg.plan.head[0][0] // 8
+    t_token = t_layer * cfg.num_layers + t_layer * head_w / layer_w
+    return {"value": 1.0 / t_token, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/exl2_cpu.c fused dequant-GEMV on one decoder layer (7 matrices, {layer_w / 1e6:.0f} MB packed), "
+                      f"{n} repeats, x{cfg.num_layers} layers + head by bytes", "ms_per_layer": t_layer * 1e3}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# arms
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  The reference has no CPU
+    q_gemm, so this is the oracle port (kind "port"), each step = one bounded one-layer sample."""
+    if rank != 0:
+        return
+    from exllamav2_b200.model import PRESETS
+    cfg = PRESETS[args.model]()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_port_baseline(cfg, budget_s=max(0.25, 90.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(r)
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[-1])
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32 accumulate over int weights",
+            "data": "synthetic", "config": {"workload": f"{cfg.name} decode bs=1 (CPU port of q_gemm, weights only)"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    from exllamav2_b200 import ext as ext_c
+    from exllamav2_b200.model import PRESETS, ExLlamaV2Decoder
+    if world > 1:
+        from exllamav2_b200 import tensor_p
+        return tensor_p.run_bench(args, rank, world, METRIC, UNIT)
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    cfg = PRESETS[args.model]()
+    t_build = time.time()
+    dec = ExLlamaV2Decoder(cfg, dev, seed=0, batch_size=1, cache_len=1024)
+    torch.cuda.synchronize()
+    t_build = time.time() - t_build
+    g = torch.Generator(device="cpu").manual_seed(0)
+    prompt = torch.randint(0, cfg.vocab_size, (1, args.prompt_len), generator=g).to(dev)
+    dec.prefill(prompt)
+    torch.cuda.synchronize()
+
+    # graph: decode step + on-device greedy pick feeding the next step (fully device-resident loop)
+    def step_with_argmax():
+        dec._decode_step()
+        torch.argmax(dec.logits, dim=-1, keepdim=True, out=dec.ids)
+
+    saved = dec.cache.cache_seqlens.clone()
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        step_with_argmax()
+        torch.cuda.synchronize()
+        dec.cache.cache_seqlens.copy_(saved)
+        l0 = ext_c.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            step_with_argmax()
+        launches_per_step = ext_c.launch_count() - l0
+    torch.cuda.synchronize()
+    dec.cache.cache_seqlens.copy_(saved)
+    dec.ids.copy_(prompt[:, -1:])
+
+    W, K = max(3, args.warmup), args.steps
+    assert args.prompt_len + 2 * (W + K) + 8 < dec.cache.max_seq_len
+    for _ in range(W):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    ms_per_step = ms_total / K
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e: host buffers every step --------------------------------------------------------------------------
+    dec.capture()     # plain decode graph (no device argmax)
+    ids_host = torch.zeros((1, 1), dtype=torch.long).pin_memory()
+    logits_host = torch.empty((1, cfg.vocab_size), dtype=torch.half).pin_memory()
+    ids_host[0, 0] = int(dec.ids[0, 0].item())
+    for _ in range(3):
+        dec.ids.copy_(ids_host, non_blocking=True)
+        dec.graph.replay()
+        logits_host.copy_(dec.logits, non_blocking=True)
+        torch.cuda.synchronize()
+        ids_host[0, 0] = int(torch.argmax(logits_host.float(), dim=-1)[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        dec.ids.copy_(ids_host, non_blocking=True)
+        dec.graph.replay()
+        logits_host.copy_(dec.logits, non_blocking=True)
+        torch.cuda.synchronize()
+        ids_host[0, 0] = int(torch.argmax(logits_host.float(), dim=-1)[0])
+    t_e2e = (time.perf_counter() - t0) / K
+    e2e = {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": cfg.vocab_size * 2,
+           "ms_per_step": t_e2e * 1e3}
+
+    # ---- roofline of the dominant kernel: exactly the model's GEMV launches, back to back ------------------------
+    x = torch.randn((1, cfg.hidden_size), dtype=torch.half, device=dev)
+    qkv = [torch.empty((1, n), dtype=torch.half, device=dev) for n in (cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim)]
+    ao = torch.randn((1, 1, cfg.num_heads * cfg.head_dim), dtype=torch.half, device=dev)
+    xs = torch.zeros((1, 1, cfg.hidden_size), dtype=torch.half, device=dev)
+    sin, cos = dec.sin, dec.cos
+
+    nt = ext_c.none_tensor
+    norope = [ext_c.make_q_attn(L.input_norm, nt, True, False, cfg.norm_eps, L.q_proj.q_handle, L.k_proj.q_handle, L.v_proj.q_handle,
+                                L.o_proj.q_handle, nt, nt, 64, cfg.hidden_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
+                                cfg.max_seq_len, False, 0, cfg.head_dim, nt, nt, nt, nt, False, True) for L in dec.layers]
+
+    def gemv_only():
+        for L, A in zip(dec.layers, norope):
+            ext_c.q_attn_forward_1(A, xs, 1, 1, 0, nt, qkv[0], qkv[1], qkv[2], sin, cos)    # RMSNorm + Q|K|V GEMV (one launch)
+            ext_c.q_attn_forward_2(A, xs, ao, 1, 1)                                         # O GEMV
+            ext_c.q_mlp_forward_(L.mlp, xs)                                                 # gate|up GEMV (+silu*mul), down GEMV
+        ext_c.gemm_half_q_half(x, dec.lm_head.q_handle, dec.logits, False)
+
+    with torch.cuda.stream(s):
+        gemv_only()
+        torch.cuda.synchronize()
+        l0 = ext_c.launch_count()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, stream=s):
+            gemv_only()
+        n_launch_roof = ext_c.launch_count() - l0
+    n_gemv = 4 * cfg.num_layers + 1
+    for _ in range(3):
+        g2.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    R = 20
+    for _ in range(R):
+        g2.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_gemv = e0.elapsed_time(e1) / R
+    peak, peak_src = measured_peaks()
+    achieved = dec.weight_bytes / (ms_gemv * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_token": dec.weight_bytes,
+                "gemv_launches_per_token": n_gemv, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
+                "note": f"{n_launch_roof} gemv launches replayed back to back in one CUDA graph, CUDA events"}
+
+    cpu = cpu_port_baseline(cfg) if not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16 (int2-8 weights, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": f"{cfg.name} single-stream decode, {args.prompt_len}-token prompt, Q4 KV cache, bs=1",
+                   "l2": "inputs_exceed_l2 (3.3 GB of weights per step)", "weight_bytes": dec.weight_bytes, "build_s": round(t_build, 1),
+                   "bpw_layers": "attn [5,4]@.1/.9 g128; mlp 3/4 layers [5,4], 1/4 [4,3]; head 6-bit"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama2-7b-4.0bpw")
+    ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -235,9 +235,9 @@ def test_q_mlp_block(rows):
     from exllamav2_b200 import ext as ext_c
     from exllamav2_b200.ext import none_tensor
     hidden, inter = 256, 704       # 704 = 11 strips of 64
-    wg = synth.make_exl2(hidden, inter, (4, 3), (0.1, 0.9), 128, seed=5)
-    wu = synth.make_exl2(hidden, inter, (4,), (1.0,), 32, seed=6)
-    wd = synth.make_exl2(inter, hidden, (6, 5), (0.1, 0.9), 32, seed=7, scale_max_range=(0.2, 0.6))
+    wg = synth.make_exl2(hidden, inter, (4, 3), (0.1, 0.9), 128, seed=5, scale_max_range=(0.02, 0.08))
+    wu = synth.make_exl2(hidden, inter, (4,), (1.0,), 32, seed=6, scale_max_range=(0.02, 0.08))
+    wd = synth.make_exl2(inter, hidden, (6, 5), (0.1, 0.9), 32, seed=7, scale_max_range=(0.02, 0.08))
     Wg, Wu, Wd = oracle.exl2_reconstruct(wg), oracle.exl2_reconstruct(wu), oracle.exl2_reconstruct(wd)
     lg, lu, ld = _lin(wg, hidden, inter), _lin(wu, hidden, inter), _lin(wd, inter, hidden)
     rng = np.random.default_rng(rows + 50)
