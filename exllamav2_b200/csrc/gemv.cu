@@ -38,6 +38,34 @@ __host__ __device__ __forceinline__ int run_max(int bits) { return STAGE_BYTES /
 
 __device__ __forceinline__ int cta_of_unit(long long x, long long G, long long U) { return (int)(((x + 1) * G - 1) / U); }
 
+// Everything about slab `ks` from the matrix's region descriptors (kernel parameters, no memory access).
+struct SlabInfo {
+    int bits, group, left;     // left = slabs until the region ends (>= 1)
+    uint32_t off;
+};
+__device__ __forceinline__ SlabInfo slab_info(const QMatView& w, int ks) {
+    int r = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_REGIONS; ++i)
+        if (i < w.num_regions && ks >= w.reg[i].ks_begin) r = i;
+    const QRegion& R = w.reg[r];
+    const int d = ks - R.ks_begin;
+    const int end = (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS;
+    SlabInfo s;
+    s.bits = R.bits;
+    s.group = R.group_base + (d >> R.spg_log2);
+    s.left = end - ks;
+    s.off = R.off_base + (uint32_t)d * (uint32_t)slab_bytes(R.bits);
+    return s;
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = clock64(); P.dbg[8 + (i)] = gtimer(); } } while (0)
+
 // ---- per-slab math ---------------------------------------------------------------------------------------------
 
 template <int BITS>
@@ -115,6 +143,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
     const int g = lane >> 2, t = lane & 3;
 
     griddep_launch_dependents();   // let the next kernel in the stream start prefetching its weights
+    DBG_STAMP(0);
 
     const uint32_t smem0 = smem_addr(smem);
     const uint32_t ring = smem0 + warp * RING_BYTES;
@@ -152,13 +181,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         // ---- producer: fill the ring (weights never depend on a previous kernel) ----
         int fetch_ks = wk0, fstage = 0, cstage = 0;
         auto issue = [&]() {
-            const uint2 tab = __ldg(w.slab_tab + fetch_ks);
-            const int bits = (tab.y >> 16) & 0xF;
-            const int run = min(min(run_max(bits), (int)(tab.y >> 20)), wk1 - fetch_ks);
-            const uint32_t bytes = (uint32_t)run * slab_bytes(bits);
+            const SlabInfo si = slab_info(w, fetch_ks);
+            const int run = min(min(run_max(si.bits), si.left), wk1 - fetch_ks);
+            const uint32_t bytes = (uint32_t)run * slab_bytes(si.bits);
             if (lane == 0) {
                 mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
-                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + tab.x, bytes, bars + 8 * fstage);
+                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + si.off, bytes, bars + 8 * fstage);
             }
             fetch_ks += run;
             fstage = (fstage + 1 == STAGES) ? 0 : fstage + 1;
@@ -166,44 +194,114 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 #pragma unroll 1
         for (int s = 0; s < STAGES && fetch_ks < wk1; ++s) issue();
 
+        // static data of the activation gather, fetched BEFORE the dependency wait: the permutation entries of the
+        // rows this thread stages (q_perm never changes) and, with the norm folded in, the norm weights
+        constexpr int PRE = 8;
+        const int rows = seg * SLAB_K, k0 = ks0 * SLAB_K;
+        int src_pre[PRE];
+        half nw_pre[PRE];
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            const int r = tid + j * GEMV_THREADS;
+            src_pre[j] = 0;
+            nw_pre[j] = __float2half(0.f);
+            if (r < rows) {
+                src_pre[j] = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
+            }
+        }
+        if (P.norm_w) {
+#pragma unroll
+            for (int j = 0; j < PRE; ++j)
+                if (tid + j * GEMV_THREADS < rows) nw_pre[j] = __ldg(P.norm_w + src_pre[j]);
+        }
+        DBG_STAMP(1);
+
         if (first_seg) griddep_wait();   // from here on we may read what the previous kernel wrote
+        DBG_STAMP(2);
 
         // ---- stage activations a'[m][r] = f(x[m][perm[k0+r]]) for the segment's rows ----
         if (first_seg && P.norm_w) {
             // RMSNorm statistics per token (cuda/rms_norm.cu:55-111): clamp, fp32 sum of squares, rsqrt(mean+eps)
             const int K = w.K;
-            for (int m = warp; m < M; m += GEMV_WARPS) {
-                const half* xr = mt.x + (size_t)m * mt.ldx;
+            if (M == 1) {
+                // single token: all 256 threads share the row, 128-bit loads
+                const half* xr = mt.x;
                 float sum = 0.f;
-                for (int k = lane * 2; k < K; k += 64) {
-                    const half2 x2 = *reinterpret_cast<const half2*>(xr + k);
-                    float f0 = fmaxf(-65504.f, fminf(__low2float(x2), 65504.f));
-                    float f1 = fmaxf(-65504.f, fminf(__high2float(x2), 65504.f));
-                    sum = fmaf(f0, f0, sum);
-                    sum = fmaf(f1, f1, sum);
+                for (int k = tid * 8; k < K; k += GEMV_THREADS * 8) {
+                    const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
+                    const half2* h2 = reinterpret_cast<const half2*>(&v4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
+                        float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
+                        sum = fmaf(f0, f0, sum);
+                        sum = fmaf(f1, f1, sum);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
+                float* part = reinterpret_cast<float*>(smem + SMEM_RINGS + SMEM_BARS + 36);   // 7 floats after flag
+                if (lane == 0) rstd_s[warp] = sum;          // reuse rstd_s[0..7] as partial sums
+                __syncthreads();
+                float tot = 0.f;
+#pragma unroll
+                for (int i = 0; i < GEMV_WARPS; ++i) tot += rstd_s[i];
+                __syncthreads();
+                if (tid == 0) rstd_s[0] = rsqrtf(tot * (1.0f / (float)K) + P.norm_eps);
+                (void)part;
+            } else {
+                for (int m = warp; m < M; m += GEMV_WARPS) {
+                    const half* xr = mt.x + (size_t)m * mt.ldx;
+                    float sum = 0.f;
+                    for (int k = lane * 8; k < K; k += 256) {
+                        const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
+                        const half2* h2 = reinterpret_cast<const half2*>(&v4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
+                            float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
+                            sum = fmaf(f0, f0, sum);
+                            sum = fmaf(f1, f1, sum);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
+                }
             }
             __syncthreads();
         }
         {
-            const int rows = seg * SLAB_K, k0 = ks0 * SLAB_K;
-            for (int idx = tid; idx < rows * M; idx += GEMV_THREADS) {
-                const int m = idx / rows, r = idx - m * rows;
-                const int kp = k0 + r;
-                const int src = w.perm ? (int)__ldg(w.perm + kp) : kp;
-                half v = mt.x[(size_t)m * mt.ldx + src];
-                if (P.norm_w) {
-                    float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
-                    v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
+            // every thread stages rows r = tid + j*256 for all M tokens; all loads of a thread are independent
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) {
+                const int r = tid + j * GEMV_THREADS;
+                if (r < rows) {
+                    for (int m = 0; m < M; ++m) {
+                        half v = mt.x[(size_t)m * mt.ldx + src_pre[j]];
+                        if (P.norm_w) {
+                            float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
+                            v = __float2half_rn(xf * __half2float(nw_pre[j]) * rstd_s[m]);
+                        }
+                        *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
+                    }
                 }
-                *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
+            }
+            for (int r = tid + PRE * GEMV_THREADS; r < rows; r += GEMV_THREADS) {     // long segments (K > 2048 rows)
+                const int src = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
+                for (int m = 0; m < M; ++m) {
+                    half v = mt.x[(size_t)m * mt.ldx + src];
+                    if (P.norm_w) {
+                        float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
+                        v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
+                    }
+                    *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
+                }
             }
         }
         first_seg = false;
         __syncthreads();
+        DBG_STAMP(3);
 
         // ---- consumer ----
         float acc_tot[2][2][4], acc_g[2][2][4];
@@ -263,16 +361,16 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 
         int cons_ks = wk0;
         while (cons_ks < wk1) {
-            const uint2 tab = __ldg(w.slab_tab + cons_ks);
-            const int bits = (tab.y >> 16) & 0xF;
-            const int run = min(min(run_max(bits), (int)(tab.y >> 20)), wk1 - cons_ks);
+            const SlabInfo si0 = slab_info(w, cons_ks);
+            const int bits = si0.bits;
+            const int run = min(min(run_max(bits), si0.left), wk1 - cons_ks);
             mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
             phases ^= 1u << cstage;
             const uint32_t sbase = ring + cstage * STAGE_BYTES;
 #pragma unroll 1
             for (int i = 0; i < run; ++i) {
                 const int ks = cons_ks + i;
-                const int grp = (int)(__ldg(&w.slab_tab[ks].y) & 0xFFFFu);
+                const int grp = slab_info(w, ks).group;
                 if (grp != cur_group) {
                     if (cur_group >= 0) flush();
                     enter_group(grp);
@@ -305,6 +403,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 
         // ---- cross-warp reduction (the ring memory is idle now) ----
         __syncthreads();
+        DBG_STAMP(4);
         {
             float* red = reinterpret_cast<float*>(smem + warp * RING_BYTES);
 #pragma unroll
@@ -405,11 +504,16 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
             }
         }
         __syncthreads();      // ring / act memory is reused by the next segment
+        DBG_STAMP(5);
         u += seg;
     }
 }
 
 // ---- host launcher -----------------------------------------------------------------------------------------------
+
+int g_ctas_per_sm = 1;      // 1 leaves room for the NEXT kernel's CTA (PDL weight prefetch) on every SM
+unsigned long long* g_dbg = nullptr;
+int g_dbg_cta = 0;
 
 struct DeviceWorkspace {
     float* ws = nullptr;
@@ -461,6 +565,7 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
         units += mats[i].w.strips * P.KS;
         strips += mats[i].w.strips;
     }
+    if (norm_w) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
     if (epilogue != EPI_STORE)
         EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
     P.total_units = units;
@@ -469,9 +574,11 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     P.epilogue = epilogue;
     P.ws = dw->ws;
     P.counters = dw->counters;
+    P.dbg = g_dbg;
+    P.dbg_cta = g_dbg_cta;
 
     const int sms = device_sm_count(device);
-    const int grid = std::max(1, std::min(2 * sms, units));
+    const int grid = std::max(1, std::min(sms * g_ctas_per_sm, units));
     const int seg_max = std::min(P.KS, (units + grid - 1) / grid);
     P.act_rows = seg_max * SLAB_K;
     P.act_stride = ((P.act_rows * 2 + 127) / 128) * 128 + 64;
@@ -535,4 +642,12 @@ extern "C" int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_
     cudaFreeAsync(dc, stream);
     EXL2B_CUDA(cudaStreamSynchronize(stream));
     return rc;
+}
+
+// ---- tuning / diagnostics hooks (not part of the reference surface) ---------------------------------------------------
+extern "C" int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta) {
+    if (ctas_per_sm > 0) exl2b::g_ctas_per_sm = ctas_per_sm;
+    exl2b::g_dbg = stamps;
+    exl2b::g_dbg_cta = cta;
+    return 0;
 }

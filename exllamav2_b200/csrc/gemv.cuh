@@ -38,6 +38,8 @@ struct GemvParams {
     int maxc;              // max contributors per strip (workspace stride)
     int act_stride;        // bytes between token rows of the staged activations in shared memory
     int act_rows;          // rows staged per segment (capacity)
+    unsigned long long* dbg;   // optional phase timestamps (globaltimer) of CTA dbg_cta, NULL in production
+    int dbg_cta;
 };
 
 // Launch one or more passes (8 tokens each) of the GEMV over `nm` matrices that share K and the input layout.

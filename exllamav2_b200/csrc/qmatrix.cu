@@ -225,13 +225,52 @@ static int build_tables_exl2(const exl2b_qmatrix_desc* d, const uint16_t* hg, st
         off += slab_bytes(ginfo[gi].bits);
     }
     strip_bytes = off;
+    return 0;
+}
+
+// Group structure -> at most MAX_REGIONS arithmetic regions (same bits, same power-of-two group size; a short last
+// group may close a region).  Converter output always fits (conversion/qparams.py: <= 3 bit widths per matrix).
+static int build_regions(QMatView& v, const std::vector<uint2>& tab, const std::vector<int>& group_rows) {
+    v.num_regions = 0;
+    int ks = 0;
+    const int KS = v.KS;
+    while (ks < KS) {
+        const int bits = (tab[ks].y >> 16) & 0xF, g0 = tab[ks].y & 0xFFFF;
+        const int rows = group_rows[g0];
+        int spg = rows / SLAB_K, lg = 0;
+        while ((1 << lg) < spg) ++lg;
+        EXL2B_REQUIRE((1 << lg) == spg || g0 == v.groups - 1, "group of %d rows: group sizes must be 32 * 2^n", rows);
+        EXL2B_REQUIRE(v.num_regions < MAX_REGIONS, "more than %d (bits, group size) regions in one matrix", MAX_REGIONS);
+        QRegion& r = v.reg[v.num_regions++];
+        r.ks_begin = ks;
+        r.bits = bits;
+        r.spg_log2 = lg;
+        r.group_base = g0;
+        r.off_base = tab[ks].x;
+        // extend while groups keep the same bits and size (the last group of the matrix may be shorter)
+        int g = g0;
+        while (ks < KS) {
+            const int gg = tab[ks].y & 0xFFFF;
+            if (gg != g) {
+                const int b2 = (tab[ks].y >> 16) & 0xF, rows2 = group_rows[gg];
+                const bool same = b2 == bits && (rows2 == rows || (gg == v.groups - 1 && rows2 < rows));
+                if (!same || gg != g + 1) break;
+                g = gg;
+            }
+            ++ks;
+        }
+    }
+    return 0;
+}
+
+static void fill_left_same(std::vector<uint2>& tab) {
+    const int KS = (int)tab.size();
     int left = 0;
     for (int ks = KS - 1; ks >= 0; --ks) {   // slabs left (incl. this one) with the same bit width
         const uint32_t b = (tab[ks].y >> 16) & 0xF;
         left = (ks + 1 < KS && ((tab[ks + 1].y >> 16) & 0xF) == b) ? left + 1 : 1;
         tab[ks].y |= (uint32_t)std::min(left, 4095) << 20;
     }
-    return 0;
 }
 
 }  // namespace exl2b
@@ -300,6 +339,11 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
         }
         int rc = build_tables_exl2(d, hg.data(), m->slab_tab_host, ginfo, m->bits_mask, v.strip_bytes);
         if (rc) return fail(rc);
+        std::vector<int> group_rows(d->groups);
+        for (int i = 0; i < d->groups; ++i) group_rows[i] = (i + 1 < d->groups ? ginfo[i + 1].row0 : v.K) - ginfo[i].row0;
+        rc = build_regions(v, m->slab_tab_host, group_rows);
+        if (rc) return fail(rc);
+        fill_left_same(m->slab_tab_host);
         const uint64_t expect_rows = (uint64_t)v.strip_bytes / 256;   // sum over slabs of bits == packed rows
         if (d->q_weight_rows && (uint64_t)d->q_weight_rows != expect_rows) {
             set_error("q_weight has %d rows, groups imply %llu", d->q_weight_rows, (unsigned long long)expect_rows);
@@ -316,6 +360,13 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
             m->slab_tab_host[ks].y = (uint32_t)(ks * SLAB_K / gptq_gs) | (4u << 16) | ((uint32_t)std::min(v.KS - ks, 4095) << 20);
         }
         v.strip_bytes = (uint32_t)v.KS * slab_bytes(4);
+        {
+            int lg = 0;
+            while ((SLAB_K << lg) < gptq_gs) ++lg;
+            if ((SLAB_K << lg) != gptq_gs) { set_error("GPTQ group size %d must be 32 * 2^n", gptq_gs); return fail(-2); }
+            v.num_regions = 1;
+            v.reg[0] = QRegion{0, 4, lg, 0, 0u};
+        }
         // act-order: stable group-sorted permutation, q_matrix.cu:597-647
         if (d->gptq_g_idx) {
             if (!d->q_perm || !d->q_invperm) { set_error("act-order GPTQ needs q_perm/q_invperm buffers"); return fail(-2); }

@@ -6,6 +6,17 @@
 
 namespace exl2b {
 
+// A run of slabs with one bit width and one (power-of-two) group size: everything about slab ks in the region is
+// arithmetic on kernel parameters -- no table load sits on the GEMV's critical path.
+struct QRegion {
+    int ks_begin;        // first slab of the region (the region ends where the next one begins, or at KS)
+    int bits;
+    int spg_log2;        // log2(slabs per group)
+    int group_base;      // group index of the region's first slab
+    uint32_t off_base;   // byte offset of the region's first slab inside a strip
+};
+constexpr int MAX_REGIONS = 6;
+
 // Device-side view handed to kernels by value.
 struct QMatView {
     const uint32_t* packed;       // [strips][strip_bytes]  private layout
@@ -20,6 +31,8 @@ struct QMatView {
     uint32_t strip_bytes;
     int K, N, KS, strips, groups;
     int is_gptq;
+    int num_regions;
+    QRegion reg[MAX_REGIONS];
 };
 
 struct QMatrix {

@@ -148,6 +148,18 @@ int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, 
  * pageable); the call copies a to the device, runs gemm_half_q_half, copies c back and waits. */
 int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_host, uint16_t* c_host, int m, exl2b_stream_t stream);
 
+/* Tuning / diagnostics hook (no reference counterpart): CTAs per SM of the GEMV grid (<= 0 keeps the current value)
+ * and an optional device buffer of 8 uint64 that receives globaltimer phase stamps of CTA `cta` (NULL disables). */
+int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta);
+
+/* Stand-in for flash_attn_with_kvcache (third-party in the reference, attn.py:602-613): appends the q_len new K/V rows
+ * to the paged fp16 cache at [seqlen, seqlen+q_len) and attends causally.  q [batch,q_len,H,hd], k/v_new
+ * [batch,q_len,KVH,hd], caches fp16 [pages,page_size,KVH,hd], out [batch,q_len,H,hd]; head_dim 64 or 128. */
+int exl2b_paged_attn_decode(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint16_t* k_cache,
+                            uint16_t* v_cache, const int32_t* cache_seqlens, const int32_t* block_table, uint16_t* out,
+                            int batch, int q_len, int num_heads, int num_kv_heads, int head_dim, int page_size,
+                            int pages_per_seq, float softmax_scale, exl2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

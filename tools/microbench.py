@@ -58,7 +58,13 @@ def main():
     ap.add_argument("--m", default="1,8")
     ap.add_argument("--total-mb", type=int, default=512)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--phases", action="store_true", help="print per-phase clock stamps of one CTA of the GEMV kernel")
     args = ap.parse_args()
+    import ctypes
+    ext_c.lib.exl2b_debug_set.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    if args.ctas_per_sm:
+        ext_c.lib.exl2b_debug_set(args.ctas_per_sm, None, 0)
     ref = None
     if args.ref:
         from build_ref import load_ref
@@ -104,6 +110,17 @@ def main():
                 for h in handles:
                     ext_c.gemm_half_q_half(a, h, c, False)
 
+            if args.phases:
+                stamps = torch.zeros((16,), dtype=torch.int64, device=DEV)
+                for cta in (0, 73, 147):
+                    ext_c.lib.exl2b_debug_set(0, stamps.data_ptr(), cta)
+                    run_new()
+                    torch.cuda.synchronize()
+                    st = stamps.cpu().tolist()
+                    clk = [st[i] - st[0] for i in range(6)]
+                    ns = [st[8 + i] - st[8] for i in range(6)]
+                    print(json.dumps({"shape": name, "M": M, "cta": cta, "phase_clk[start,prefetch,wait,staged,consumed,done]": clk, "phase_ns": ns}), flush=True)
+                ext_c.lib.exl2b_debug_set(0, None, 0)
             t_eager = time_loop(run_new, 5)
             # graph-captured cycle (no host launch overhead)
             g = torch.cuda.CUDAGraph()
