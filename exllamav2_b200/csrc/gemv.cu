@@ -8,8 +8,9 @@
 //   * inside a CTA each of the 8 warps owns a contiguous sub-range of the segment and is its own producer and
 //     consumer: lane 0 issues cp.async.bulk (TMA 1-D) copies of whole slabs into the warp's private 3-stage
 //     shared-memory ring, completion on per-stage mbarriers; no CTA-wide barrier in the main loop.
-//   * the first ring fill is issued BEFORE griddepcontrol.wait: with programmatic dependent launch the weights
-//     of this GEMV are already in flight while the previous kernel (which produces our activations) drains.
+//   * everything static (weights, permutation entries, norm weights) is requested BEFORE griddepcontrol.wait: with
+//     programmatic dependent launch this GEMV's weights are in flight while the previous kernel (which produces our
+//     activations) drains.  All slab bookkeeping is arithmetic on kernel parameters (QRegion), never a table load.
 //   * activations are gathered through q_perm (optionally with the RMSNorm folded in) into shared memory once
 //     per segment; weights are unpacked in the fp16 domain straight into mma.m16n8k16 A fragments, tokens are
 //     the N=8 dimension, accumulation is fp32 in registers, group scales are applied per group in fp32.
@@ -29,93 +30,54 @@ constexpr int GEMV_THREADS = GEMV_WARPS * 32;
 constexpr int STAGE_BYTES = 4096;
 constexpr int STAGES = 3;
 constexpr int RING_BYTES = STAGE_BYTES * STAGES;          // per warp
-constexpr int RED_FLOATS = GEMV_MTOK * STRIP_N;           // 512 floats = 2 KB per warp, aliases the ring
 constexpr int SMEM_RINGS = GEMV_WARPS * RING_BYTES;       // 96 KB
 constexpr int SMEM_BARS = GEMV_WARPS * STAGES * 8;
-constexpr int SMEM_MISC = 64;                              // rstd[8] + flags
+constexpr int SMEM_MISC = 64;                              // rstd[8] + flag
+constexpr int RED_FLOATS = GEMV_MTOK * STRIP_N;           // workspace floats per (strip, contributor)
 
 __host__ __device__ __forceinline__ int run_max(int bits) { return STAGE_BYTES / slab_bytes(bits); }
 
-__device__ __forceinline__ int cta_of_unit(long long x, long long G, long long U) { return (int)(((x + 1) * G - 1) / U); }
+__device__ __forceinline__ int cta_of_unit(unsigned x, unsigned G, unsigned U) { return (int)(((x + 1u) * G - 1u) / U); }
 
-// Everything about slab `ks` from the matrix's region descriptors (kernel parameters, no memory access).
-struct SlabInfo {
-    int bits, group, left;     // left = slabs until the region ends (>= 1)
-    uint32_t off;
-};
-__device__ __forceinline__ SlabInfo slab_info(const QMatView& w, int ks) {
+__device__ __forceinline__ int region_of(const QMatView& w, int ks) {
     int r = 0;
 #pragma unroll
     for (int i = 1; i < MAX_REGIONS; ++i)
         if (i < w.num_regions && ks >= w.reg[i].ks_begin) r = i;
-    const QRegion& R = w.reg[r];
-    const int d = ks - R.ks_begin;
-    const int end = (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS;
-    SlabInfo s;
-    s.bits = R.bits;
-    s.group = R.group_base + (d >> R.spg_log2);
-    s.left = end - ks;
-    s.off = R.off_base + (uint32_t)d * (uint32_t)slab_bytes(R.bits);
-    return s;
+    return r;
 }
+__device__ __forceinline__ int region_end(const QMatView& w, int r) { return (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS; }
 
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = clock64(); P.dbg[8 + (i)] = gtimer(); } } while (0)
+#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = clock64(); } } while (0)
 
 // ---- per-slab math ---------------------------------------------------------------------------------------------
 
 template <int BITS>
-__device__ __forceinline__ void load_lane_words(uint32_t base, int lane, uint32_t* mw, uint32_t* ew) {
+__device__ __forceinline__ void load_lane_words(const uint8_t* base, int lane, uint32_t* mw, uint32_t* ew) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
     if constexpr (Pm == 8) {
-        uint4 a = lds128(base + lane * 16), b = lds128(base + 512 + lane * 16);
+        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16), b = *reinterpret_cast<const uint4*>(base + 512 + lane * 16);
         mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
     } else if constexpr (Pm == 4) {
-        uint4 a = lds128(base + lane * 16);
+        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16);
         mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w;
     } else {
-        uint2 a = lds64(base + lane * 8);
+        const uint2 a = *reinterpret_cast<const uint2*>(base + lane * 8);
         mw[0] = a.x; mw[1] = a.y;
     }
     if constexpr (Pe == 1) {
-        ew[0] = lds32(base + 128 * Pm + lane * 4);
+        ew[0] = *reinterpret_cast<const uint32_t*>(base + 128 * Pm + lane * 4);
     } else if constexpr (Pe == 2) {
-        uint2 a = lds64(base + 128 * Pm + lane * 8);
+        const uint2 a = *reinterpret_cast<const uint2*>(base + 128 * Pm + lane * 8);
         ew[0] = a.x; ew[1] = a.y;
     }
 }
 
-// one slab (2 blocks) of an EXL2 strip: acc[blk][sub] += W(16x32 tile)^T-fragments * B
-template <int BITS>
-__device__ __forceinline__ void slab_exl2(uint32_t sm, int lane, const uint32_t (&B)[4], float (&acc)[2][2][4]) {
+__device__ __forceinline__ void mma_block(float (&acc)[2][4], const uint32_t* A, const uint32_t (&B)[4]) {
 #pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-        uint32_t mw[8], ew[2], A[16];
-        load_lane_words<BITS>(sm + blk * block_bytes(BITS), lane, mw, ew);
-        dequant_block_exl2<BITS>(mw, ew, A);
+    for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) mma16816(acc[blk][sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
-    }
-}
-
-__device__ __forceinline__ void slab_gptq(uint32_t sm, int lane, const uint32_t (&B)[4], const uint32_t (&zc)[2][4],
-                                          float (&acc)[2][2][4]) {
-#pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-        uint32_t mw[8], ew[2], A[16];
-        load_lane_words<4>(sm + blk * block_bytes(4), lane, mw, ew);
-        dequant_block_gptq(mw, zc[blk], A);
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) mma16816(acc[blk][sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
-    }
+        for (int s = 0; s < 2; ++s) mma16816(acc[sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
 }
 
 // ---- activation functions (reference arithmetic, cuda/q_mlp_activation.cuh:13-52) -------------------------------
@@ -128,11 +90,95 @@ __device__ __forceinline__ half gelu_h(half x) {
     float xf = __half2float(x);
     const float c = 0.797884560803f;
     float t = c * (xf + 0.044715f * xf * xf * xf);
-    // tanh_opt of the reference (cuda/q_mlp_activation.cuh:4-11): tanh.approx on sm_75+
-    float th;
+    float th;   // tanh_opt of the reference (cuda/q_mlp_activation.cuh:4-11): tanh.approx on sm_75+
     asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
     xf = 0.5f * xf * (1.0 + th);
     return __float2half_rn(xf);
+}
+
+// Per-warp accumulation state of one segment.
+struct WarpAcc {
+    float tot[2][2][4];     // [blk][sub][mma c-reg]
+    float grp[2][2][4];     // accumulates the current group only
+    uint32_t sw[8];         // EXL2: scale words of (group, strip); GPTQ: zero words
+    half gsc[8];            // GPTQ: fp16 scales of the lane's 8 columns
+    uint32_t zc[2][4];      // GPTQ: per-row zero constants (half2 bits)
+    half smax;
+    int cur_group;
+};
+
+__device__ __forceinline__ void acc_flush(WarpAcc& a, const QMatView& w, int g) {     // tot += scale(group, n) * grp
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int j = 4 * blk + 2 * sub + rr;
+                float s;
+                if (!w.is_gptq) {
+                    const int q = (int)((a.sw[j] >> (4 * g)) & 15u) + 1;
+                    s = __half2float(__hmul(__int2half_rn(q * q), a.smax));     // fp16 scale, qdq_util.cuh:24-30
+                } else {
+                    s = __half2float(a.gsc[j]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    a.tot[blk][sub][2 * rr + e] = fmaf(s, a.grp[blk][sub][2 * rr + e], a.tot[blk][sub][2 * rr + e]);
+                    a.grp[blk][sub][2 * rr + e] = 0.f;
+                }
+            }
+}
+
+__device__ __forceinline__ void acc_enter_group(WarpAcc& a, const QMatView& w, int grp, int strip, int g) {
+    a.cur_group = grp;
+    const int n_words = w.N >> 3;
+    const uint32_t* src = (w.is_gptq ? w.qzeros : w.q_scale) + (size_t)grp * n_words + strip * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.sw[j] = (strip * 8 + j < n_words) ? __ldg(src + j) : 0u;
+    if (!w.is_gptq) {
+        a.smax = __ldg(w.q_scale_max + grp);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = strip * STRIP_N + (j >> 2) * 32 + ((j >> 1) & 1) * 16 + (j & 1) * 8 + g;
+            a.gsc[j] = (n < w.N) ? __ldg(w.gptq_scales + (size_t)grp * w.N + n) : __float2half(0.f);
+            const int z1 = (int)((a.sw[j] >> (4 * g)) & 15u) + 1;      // zero + 1, q_gemm_kernel_gptq.cuh:169
+            const half2 c2 = __half2half2(__int2half_rn(-(((j & 1) ? 64 : 1024) + z1)));
+            a.zc[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&c2);
+        }
+    }
+}
+
+// Consume `run` slabs of one region that sit contiguously at `sp` in shared memory.
+//   d0: index of the first slab inside its region, bptr: this lane's B-fragment source for the first slab.
+template <int BITS, bool GPTQ>
+__device__ __forceinline__ void consume_run(WarpAcc& a, const QMatView& w, const QRegion& R, const uint8_t* sp, int run, int d0,
+                                            const uint8_t* bptr, bool has_b, int strip, int lane) {
+    const int g = lane >> 2;
+    const int gmask = (1 << R.spg_log2) - 1;
+#pragma unroll 2
+    for (int i = 0; i < run; ++i) {
+        const int d = d0 + i;
+        if (a.cur_group < 0 || (d & gmask) == 0) {
+            if (a.cur_group >= 0) acc_flush(a, w, g);
+            acc_enter_group(a, w, R.group_base + (d >> R.spg_log2), strip, g);
+        }
+        uint32_t B[4] = {0u, 0u, 0u, 0u};
+        if (has_b) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bptr + i * (SLAB_K * 2));
+            B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w;
+        }
+        const uint8_t* sm = sp + i * slab_bytes(BITS);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            uint32_t mw[8], ew[2], A[16];
+            load_lane_words<BITS>(sm + blk * block_bytes(BITS), lane, mw, ew);
+            if constexpr (GPTQ) dequant_block_gptq(mw, a.zc[blk], A);
+            else dequant_block_exl2<BITS>(mw, ew, A);
+            mma_block(a.grp[blk], A, B);
+        }
+    }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
@@ -148,21 +194,22 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
     const uint32_t smem0 = smem_addr(smem);
     const uint32_t ring = smem0 + warp * RING_BYTES;
     const uint32_t bars = smem0 + SMEM_RINGS + warp * STAGES * 8;
+    uint8_t* ring_p = smem + warp * RING_BYTES;
     float* rstd_s = reinterpret_cast<float*>(smem + SMEM_RINGS + SMEM_BARS);
     int* flag_s = reinterpret_cast<int*>(smem + SMEM_RINGS + SMEM_BARS + 32);
     uint8_t* act_s = smem + SMEM_RINGS + SMEM_BARS + SMEM_MISC;
-    const uint32_t act0 = smem0 + SMEM_RINGS + SMEM_BARS + SMEM_MISC;
+    const int M = P.M, KS = P.KS;
+    float* red_s = reinterpret_cast<float*>(act_s + (size_t)M * P.act_stride);      // [warp][tok][64], generic proxy only
 
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+        mbar_fence_init();
     }
-    mbar_fence_init();
     __syncwarp();
 
-    const long long U = P.total_units, G = gridDim.x;
-    const int u0 = (int)((long long)blockIdx.x * U / G), u1 = (int)((long long)(blockIdx.x + 1) * U / G);
-    const int KS = P.KS, M = P.M;
+    const unsigned U = (unsigned)P.total_units, G = gridDim.x;
+    const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
 
     uint32_t phases = 0;          // parity bit per stage
     bool first_seg = true;
@@ -181,12 +228,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         // ---- producer: fill the ring (weights never depend on a previous kernel) ----
         int fetch_ks = wk0, fstage = 0, cstage = 0;
         auto issue = [&]() {
-            const SlabInfo si = slab_info(w, fetch_ks);
-            const int run = min(min(run_max(si.bits), si.left), wk1 - fetch_ks);
-            const uint32_t bytes = (uint32_t)run * slab_bytes(si.bits);
+            const int r = region_of(w, fetch_ks);
+            const QRegion& R = w.reg[r];
+            const int run = min(min(run_max(R.bits), region_end(w, r) - fetch_ks), wk1 - fetch_ks);
+            const uint32_t bytes = (uint32_t)run * slab_bytes(R.bits);
             if (lane == 0) {
                 mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
-                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + si.off, bytes, bars + 8 * fstage);
+                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * slab_bytes(R.bits),
+                              bytes, bars + 8 * fstage);
             }
             fetch_ks += run;
             fstage = (fstage + 1 == STAGES) ? 0 : fstage + 1;
@@ -205,9 +254,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
             const int r = tid + j * GEMV_THREADS;
             src_pre[j] = 0;
             nw_pre[j] = __float2half(0.f);
-            if (r < rows) {
-                src_pre[j] = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
-            }
+            if (r < rows) src_pre[j] = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
         }
         if (P.norm_w) {
 #pragma unroll
@@ -223,12 +270,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         if (first_seg && P.norm_w) {
             // RMSNorm statistics per token (cuda/rms_norm.cu:55-111): clamp, fp32 sum of squares, rsqrt(mean+eps)
             const int K = w.K;
-            if (M == 1) {
-                // single token: all 256 threads share the row, 128-bit loads
-                const half* xr = mt.x;
+            if (M == 1) {          // single token: all 256 threads share the row, 128-bit loads
                 float sum = 0.f;
                 for (int k = tid * 8; k < K; k += GEMV_THREADS * 8) {
-                    const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
+                    const uint4 v4 = *reinterpret_cast<const uint4*>(mt.x + k);
                     const half2* h2 = reinterpret_cast<const half2*>(&v4);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -240,15 +285,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                float* part = reinterpret_cast<float*>(smem + SMEM_RINGS + SMEM_BARS + 36);   // 7 floats after flag
-                if (lane == 0) rstd_s[warp] = sum;          // reuse rstd_s[0..7] as partial sums
+                if (lane == 0) red_s[warp] = sum;
                 __syncthreads();
-                float tot = 0.f;
+                if (tid == 0) {
+                    float tot = 0.f;
 #pragma unroll
-                for (int i = 0; i < GEMV_WARPS; ++i) tot += rstd_s[i];
-                __syncthreads();
-                if (tid == 0) rstd_s[0] = rsqrtf(tot * (1.0f / (float)K) + P.norm_eps);
-                (void)part;
+                    for (int i = 0; i < GEMV_WARPS; ++i) tot += red_s[i];
+                    rstd_s[0] = rsqrtf(tot * (1.0f / (float)K) + P.norm_eps);
+                }
             } else {
                 for (int m = warp; m < M; m += GEMV_WARPS) {
                     const half* xr = mt.x + (size_t)m * mt.ldx;
@@ -287,7 +331,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
                     }
                 }
             }
-            for (int r = tid + PRE * GEMV_THREADS; r < rows; r += GEMV_THREADS) {     // long segments (K > 2048 rows)
+            for (int r = tid + PRE * GEMV_THREADS; r < rows; r += GEMV_THREADS) {     // long segments (> 2048 rows)
                 const int src = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
                 for (int m = 0; m < M; ++m) {
                     half v = mt.x[(size_t)m * mt.ldx + src];
@@ -304,94 +348,39 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         DBG_STAMP(3);
 
         // ---- consumer ----
-        float acc_tot[2][2][4], acc_g[2][2][4];
+        WarpAcc a;
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc_tot[a][b][c] = 0.f, acc_g[a][b][c] = 0.f;
+                for (int c = 0; c < 4; ++c) a.tot[i][j][c] = 0.f, a.grp[i][j][c] = 0.f;
+        a.cur_group = -1;
+        a.smax = __float2half(0.f);
 
-        int cur_group = -1;
-        uint32_t sw[8];              // EXL2: 8 scale words of (group, strip); GPTQ: zero words
-        half gsc[8];                 // GPTQ: fp16 scales of the lane's 8 columns
-        half smax = __float2half(0.f);
-        uint32_t zc[2][4];
-        const int n_words = w.N >> 3;
-
-        auto flush = [&]() {         // acc_tot += scale(group, n) * acc_g ; acc_g = 0
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int j = 4 * blk + 2 * sub + rr;
-                        float s;
-                        if (!w.is_gptq) {
-                            const int q = (int)((sw[j] >> (4 * g)) & 15u) + 1;
-                            s = __half2float(__hmul(__int2half_rn(q * q), smax));   // fp16 scale, qdq_util.cuh:24-30
-                        } else {
-                            s = __half2float(gsc[j]);
-                        }
-                        acc_tot[blk][sub][2 * rr + 0] = fmaf(s, acc_g[blk][sub][2 * rr + 0], acc_tot[blk][sub][2 * rr + 0]);
-                        acc_tot[blk][sub][2 * rr + 1] = fmaf(s, acc_g[blk][sub][2 * rr + 1], acc_tot[blk][sub][2 * rr + 1]);
-                        acc_g[blk][sub][2 * rr + 0] = 0.f;
-                        acc_g[blk][sub][2 * rr + 1] = 0.f;
-                    }
-        };
-        auto enter_group = [&](int grp) {
-            cur_group = grp;
-            const uint32_t* src = (w.is_gptq ? w.qzeros : w.q_scale) + (size_t)grp * n_words + strip * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sw[j] = (strip * 8 + j < n_words) ? __ldg(src + j) : 0u;
-            if (!w.is_gptq) {
-                smax = w.q_scale_max[grp];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = strip * STRIP_N + (j >> 2) * 32 + ((j >> 1) & 1) * 16 + (j & 1) * 8 + g;
-                    gsc[j] = (n < w.N) ? w.gptq_scales[(size_t)grp * w.N + n] : __float2half(0.f);
-                    const int z1 = (int)((sw[j] >> (4 * g)) & 15u) + 1;      // zero + 1, q_gemm_kernel_gptq.cuh:169
-                    const half2 c2 = __half2half2(__int2half_rn(-(((j & 1) ? 64 : 1024) + z1)));
-                    zc[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&c2);
-                }
-            }
-        };
-
+        const bool has_b = g < M;
+        const uint8_t* bbase = act_s + (size_t)g * P.act_stride + t * 16;
         int cons_ks = wk0;
         while (cons_ks < wk1) {
-            const SlabInfo si0 = slab_info(w, cons_ks);
-            const int bits = si0.bits;
-            const int run = min(min(run_max(bits), si0.left), wk1 - cons_ks);
+            const int r = region_of(w, cons_ks);
+            const QRegion& R = w.reg[r];
+            const int bits = R.bits;
+            const int run = min(min(run_max(bits), region_end(w, r) - cons_ks), wk1 - cons_ks);
             mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
             phases ^= 1u << cstage;
-            const uint32_t sbase = ring + cstage * STAGE_BYTES;
-#pragma unroll 1
-            for (int i = 0; i < run; ++i) {
-                const int ks = cons_ks + i;
-                const int grp = slab_info(w, ks).group;
-                if (grp != cur_group) {
-                    if (cur_group >= 0) flush();
-                    enter_group(grp);
-                }
-                uint32_t B[4] = {0u, 0u, 0u, 0u};
-                if (g < M) {
-                    const uint4 b4 = lds128(act0 + g * P.act_stride + (ks - ks0) * (SLAB_K * 2) + t * 16);
-                    B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w;
-                }
-                const uint32_t sm = sbase + i * slab_bytes(bits);
-                if (w.is_gptq) {
-                    slab_gptq(sm, lane, B, zc, acc_g);
-                } else {
-                    switch (bits) {
-                        case 4: slab_exl2<4>(sm, lane, B, acc_g); break;
-                        case 5: slab_exl2<5>(sm, lane, B, acc_g); break;
-                        case 3: slab_exl2<3>(sm, lane, B, acc_g); break;
-                        case 6: slab_exl2<6>(sm, lane, B, acc_g); break;
-                        case 2: slab_exl2<2>(sm, lane, B, acc_g); break;
-                        default: slab_exl2<8>(sm, lane, B, acc_g); break;
-                    }
+            const uint8_t* sp = ring_p + cstage * STAGE_BYTES;
+            const uint8_t* bptr = bbase + (cons_ks - ks0) * (SLAB_K * 2);
+            const int d0 = cons_ks - R.ks_begin;
+            if (w.is_gptq) {
+                consume_run<4, true>(a, w, R, sp, run, d0, bptr, has_b, strip, lane);
+            } else {
+                switch (bits) {
+                    case 4: consume_run<4, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
+                    case 5: consume_run<5, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
+                    case 3: consume_run<3, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
+                    case 6: consume_run<6, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
+                    case 2: consume_run<2, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
+                    default: consume_run<8, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
                 }
             }
             __syncwarp();
@@ -399,13 +388,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
             cstage = (cstage + 1 == STAGES) ? 0 : cstage + 1;
             if (fetch_ks < wk1) issue();     // refill the stage we just drained
         }
-        if (cur_group >= 0) flush();
+        if (a.cur_group >= 0) acc_flush(a, w, g);
 
-        // ---- cross-warp reduction (the ring memory is idle now) ----
-        __syncthreads();
-        DBG_STAMP(4);
+        // ---- cross-warp reduction through a dedicated (never async-written) shared-memory region ----
         {
-            float* red = reinterpret_cast<float*>(smem + warp * RING_BYTES);
+            float* red = red_s + warp * (M * STRIP_N);
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
@@ -415,18 +402,24 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int tok = 2 * t + e;
-                            if (tok < M) red[tok * STRIP_N + 32 * blk + 16 * sub + 8 * rr + g] = acc_tot[blk][sub][2 * rr + e];
+                            if (tok < M) red[tok * STRIP_N + 32 * blk + 16 * sub + 8 * rr + g] = a.tot[blk][sub][2 * rr + e];
                         }
         }
         __syncthreads();
+        DBG_STAMP(4);
 
         const int gs = mt.strip_begin + strip;
-        const long long sb = (long long)mt.unit_begin + (long long)strip * KS;
+        const unsigned sb = (unsigned)mt.unit_begin + (unsigned)strip * KS;
         const int first_cta = cta_of_unit(sb, G, U), last_cta = cta_of_unit(sb + KS - 1, G, U);
         const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
         const bool paired = P.epilogue != EPI_STORE;
         const int n_out = M * STRIP_N;
-
+        auto warp_sum = [&](int o) {
+            float v = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < GEMV_WARPS; ++wi) v += red_s[wi * n_out + o];
+            return v;
+        };
         auto epilogue_store = [&](int o, float v) {
             const int tok = o >> 6, n = strip * STRIP_N + (o & 63);
             if (n < w.N) {
@@ -438,27 +431,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         };
 
         if (nc == 1 && !paired) {
-            for (int o = tid; o < n_out; o += GEMV_THREADS) {
-                float v = 0.f;
-#pragma unroll
-                for (int wi = 0; wi < GEMV_WARPS; ++wi) v += reinterpret_cast<const float*>(smem + wi * RING_BYTES)[o];
-                epilogue_store(o, v);
-            }
+            for (int o = tid; o < n_out; o += GEMV_THREADS) epilogue_store(o, warp_sum(o));
         } else {
             float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * RED_FLOATS;
-            for (int o = tid; o < n_out; o += GEMV_THREADS) {
-                float v = 0.f;
-#pragma unroll
-                for (int wi = 0; wi < GEMV_WARPS; ++wi) v += reinterpret_cast<const float*>(smem + wi * RING_BYTES)[o];
-                __stcg(wsp + o, v);
-            }
+            for (int o = tid; o < n_out; o += GEMV_THREADS) __stcg(wsp + o, warp_sum(o));
             __threadfence();
             __syncthreads();
             int expected = nc, cidx = gs;
             if (paired) {
                 // gate strip j and up strip j share one counter (the gate's) and are finalised together
                 const GemvMat& other = P.mat[1 - mi];
-                const long long ob = (long long)other.unit_begin + (long long)strip * KS;
+                const unsigned ob = (unsigned)other.unit_begin + (unsigned)strip * KS;
                 expected += cta_of_unit(ob + KS - 1, G, U) - cta_of_unit(ob, G, U) + 1;
                 cidx = P.mat[0].strip_begin + strip;
             }
@@ -479,8 +462,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
                 } else {
                     const GemvMat& mg = P.mat[0];
                     const GemvMat& mu = P.mat[1];
-                    const long long gb = (long long)mg.unit_begin + (long long)strip * KS;
-                    const long long ub = (long long)mu.unit_begin + (long long)strip * KS;
+                    const unsigned gb = (unsigned)mg.unit_begin + (unsigned)strip * KS;
+                    const unsigned ub = (unsigned)mu.unit_begin + (unsigned)strip * KS;
                     const int ncg = cta_of_unit(gb + KS - 1, G, U) - cta_of_unit(gb, G, U) + 1;
                     const int ncu = cta_of_unit(ub + KS - 1, G, U) - cta_of_unit(ub, G, U) + 1;
                     const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * RED_FLOATS;
@@ -495,15 +478,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
                             if (mu.w.bias) vu += __half2float(mu.w.bias[n]);
                             // the reference rounds gate and up to fp16 (temp_a / temp_b) before act_mul (q_mlp.cu:187-196)
                             const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);
-                            const half a = (P.epilogue == EPI_GELU_MUL) ? gelu_h(hg) : silu_h(hg);
-                            mg.c[(size_t)tok * mg.ldc + n] = __hmul(a, hu);
+                            const half av = (P.epilogue == EPI_GELU_MUL) ? gelu_h(hg) : silu_h(hg);
+                            mg.c[(size_t)tok * mg.ldc + n] = __hmul(av, hu);
                         }
                     }
                 }
                 if (tid == 0) P.counters[cidx] = 0u;     // ready for the next launch (stream-ordered)
             }
         }
-        __syncthreads();      // ring / act memory is reused by the next segment
+        __syncthreads();      // act / red memory is reused by the next segment
         DBG_STAMP(5);
         u += seg;
     }
@@ -511,7 +494,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 
 // ---- host launcher -----------------------------------------------------------------------------------------------
 
-int g_ctas_per_sm = 1;      // 1 leaves room for the NEXT kernel's CTA (PDL weight prefetch) on every SM
+int g_ctas_per_sm = 2;
 unsigned long long* g_dbg = nullptr;
 int g_dbg_cta = 0;
 
@@ -556,19 +539,19 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     GemvParams P = {};
     P.num_mats = nm;
     P.KS = mats[0].w.KS;
-    int units = 0, strips = 0;
+    long long units = 0;
+    int strips = 0;
     for (int i = 0; i < nm; ++i) {
         EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
         P.mat[i] = mats[i];
-        P.mat[i].unit_begin = units;
+        P.mat[i].unit_begin = (int)units;
         P.mat[i].strip_begin = strips;
-        units += mats[i].w.strips * P.KS;
+        units += (long long)mats[i].w.strips * P.KS;
         strips += mats[i].w.strips;
     }
     if (norm_w) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
     if (epilogue != EPI_STORE)
         EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
-    P.total_units = units;
     P.norm_w = norm_w;
     P.norm_eps = norm_eps;
     P.epilogue = epilogue;
@@ -578,8 +561,10 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     P.dbg_cta = g_dbg_cta;
 
     const int sms = device_sm_count(device);
-    const int grid = std::max(1, std::min(sms * g_ctas_per_sm, units));
-    const int seg_max = std::min(P.KS, (units + grid - 1) / grid);
+    const int grid = (int)std::max(1ll, std::min((long long)sms * g_ctas_per_sm, units));
+    EXL2B_REQUIRE((units + 1) * grid < (1ll << 31), "problem too large for 32-bit unit arithmetic");
+    P.total_units = (int)units;
+    const int seg_max = (int)std::min((long long)P.KS, (units + grid - 1) / grid);
     P.act_rows = seg_max * SLAB_K;
     P.act_stride = ((P.act_rows * 2 + 127) / 128) * 128 + 64;
     P.maxc = (int)(((long long)P.KS * grid) / units) + 2;
@@ -587,7 +572,8 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     EXL2B_REQUIRE((size_t)strips * P.maxc * RED_FLOATS * sizeof(float) <= dw->ws_bytes, "split-K workspace too small");
 
     const int fixed = SMEM_RINGS + SMEM_BARS + SMEM_MISC;
-    int tok_per_pass = std::min(GEMV_MTOK, (227 * 1024 - fixed) / P.act_stride);
+    const int per_tok = P.act_stride + GEMV_WARPS * STRIP_N * 4;        // staged activations + reduction scratch
+    int tok_per_pass = std::min(GEMV_MTOK, (227 * 1024 - fixed) / per_tok);
     EXL2B_REQUIRE(tok_per_pass >= 1, "K too large to stage one activation row (%d bytes)", P.act_stride);
 
     for (int m0 = 0; m0 < M; m0 += tok_per_pass) {
@@ -596,7 +582,7 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
             P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
             P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
         }
-        const size_t smem = (size_t)fixed + (size_t)P.M * P.act_stride;
+        const size_t smem = (size_t)fixed + (size_t)P.M * per_tok;
         EXL2B_CUDA(launch_pdl(gemv_kernel, dim3(grid), dim3(GEMV_THREADS), smem, stream, P));
     }
     return 0;

@@ -118,8 +118,7 @@ def main():
                     torch.cuda.synchronize()
                     st = stamps.cpu().tolist()
                     clk = [st[i] - st[0] for i in range(6)]
-                    ns = [st[8 + i] - st[8] for i in range(6)]
-                    print(json.dumps({"shape": name, "M": M, "cta": cta, "phase_clk[start,prefetch,wait,staged,consumed,done]": clk, "phase_ns": ns}), flush=True)
+                    print(json.dumps({"shape": name, "M": M, "cta": cta, "phase_clk[start,prefetch,wait,staged,consumed,done]": clk}), flush=True)
                 ext_c.lib.exl2b_debug_set(0, None, 0)
             t_eager = time_loop(run_new, 5)
             # graph-captured cycle (no host launch overhead)
