@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -47,7 +48,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("EXL2B_NO_PDL") != nullptr;     // diagnostics: plain stream-ordered launches
+    cfg.numAttrs = no_pdl ? 0 : 1;
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

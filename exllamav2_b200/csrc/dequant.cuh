@@ -27,6 +27,12 @@ __device__ __forceinline__ uint32_t h2mul_bits(uint32_t a, uint32_t b) {
     asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
+// (x & mask) | magic as ONE LOP3 (the compiler otherwise emits AND + OR when both constants are immediates)
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t mask, uint32_t magic) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(mask), "r"(magic));
+    return r;
+}
 }  // namespace exl2b
 #else
 #include <string.h>
@@ -48,6 +54,7 @@ static inline uint32_t h2mul_bits(uint32_t a, uint32_t b) {
     uint32_t hi = d_to_h(h_to_d((uint16_t)(a >> 16)) * h_to_d((uint16_t)(b >> 16)));
     return lo | (hi << 16);
 }
+static inline uint32_t and_or(uint32_t x, uint32_t mask, uint32_t magic) { return (x & mask) | magic; }
 }  // namespace exl2b
 #endif
 
@@ -79,14 +86,14 @@ EXL2B_HD void dequant_block_exl2(const uint32_t* mw, const uint32_t* ew, uint32_
     for (int p = 0; p < 16; ++p) {
         const int jm = pair_slot(Pm, p);
         const uint32_t x = mw[pair_word(Pm, p)] >> field_sh(Pm, jm);
-        const uint32_t tm = (x & field_mask(Pm, jm)) | field_magic(Pm, jm);
+        const uint32_t tm = and_or(x, field_mask(Pm, jm), field_magic(Pm, jm));
         if (Pe == 0) {
             A[p] = h2add_bits(tm, h2_const_int(PC::c_single(p, PC::zp)));
         } else {
             const int PeS = Pe ? Pe : 1;
             const int je = pair_slot(PeS, p);
             const uint32_t y = ew[pair_word(PeS, p)] >> field_sh(PeS, je);
-            const uint32_t te = (y & field_mask(PeS, je)) | field_magic(PeS, je);
+            const uint32_t te = and_or(y, field_mask(PeS, je), field_magic(PeS, je));
             const uint32_t r1 = h2fma_bits(te, h2_const_int(1 << Pm), h2_const_int(PC::k_double(p, PC::zp)));
             A[p] = h2add_bits(tm, r1);
         }
@@ -107,8 +114,28 @@ EXL2B_HD void dequant_block_gptq(const uint32_t* mw, const uint32_t* zc, uint32_
     for (int p = 0; p < 16; ++p) {
         const int jm = pair_slot(4, p);
         const uint32_t x = mw[pair_word(4, p)] >> field_sh(4, jm);
-        const uint32_t tm = (x & field_mask(4, jm)) | field_magic(4, jm);
+        const uint32_t tm = and_or(x, field_mask(4, jm), field_magic(4, jm));
         A[p] = h2add_bits(tm, zc[((p >> 3) & 1) * 2 + (p & 1)]);
+    }
+}
+
+// 4-bit fast path ("offset form"): every nibble is moved to in-halfword offset 4 so ONE mask / ONE magic serve all
+// fields and the zero point is not subtracted per weight:  A[p] = half2(64 + q).  The GEMV removes the offset per
+// group with the activation sum that an extra all-ones mma row provides:  sum a*(q - z) = sum a*(64+q) - (64+z)*sum a.
+// 3 shifts + 4 LOP3 per 8 weights (vs 1 shift + 4 LOP3 + 4 HADD2).  Exact: 64+q is an fp16 integer, products are
+// exact in the tensor core, fp32 accumulation sees operands only 16x larger than q - z.
+constexpr int OFFSET4 = 64;
+EXL2B_HD void dequant_block_4bit_offset(const uint32_t* mw, uint32_t* A) {
+    const uint32_t mask = 0x00f000f0u, magic = 0x54005400u;      // fp16 64.0 | nibble at mantissa bits 4..7 = 64 + q
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 4; ++w) {           // word w = (sub, s); slots 0..3 = mma regs 0..3
+        const uint32_t x = mw[w];
+        A[w * 4 + 0] = and_or(x << 4, mask, magic);
+        A[w * 4 + 1] = and_or(x, mask, magic);
+        A[w * 4 + 2] = and_or(x >> 4, mask, magic);
+        A[w * 4 + 3] = and_or(x >> 8, mask, magic);
     }
 }
 

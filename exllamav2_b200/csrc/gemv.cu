@@ -48,7 +48,13 @@ __device__ __forceinline__ int region_of(const QMatView& w, int ks) {
 }
 __device__ __forceinline__ int region_end(const QMatView& w, int r) { return (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS; }
 
-#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = clock64(); } } while (0)
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// diagnostics: per-launch slot of 8 u64: [0..5] phase stamps (ns) of CTA dbg_cta, [6] min start, [7] max end over all CTAs
+#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = gtimer(); } } while (0)
 
 // ---- per-slab math ---------------------------------------------------------------------------------------------
 
@@ -100,11 +106,12 @@ __device__ __forceinline__ half gelu_h(half x) {
 struct WarpAcc {
     float tot[2][2][4];     // [blk][sub][mma c-reg]
     float grp[2][2][4];     // accumulates the current group only
+    float sacc[4];          // 4-bit offset form: sum of the group's activations per token (all-ones mma row)
     uint32_t sw[8];         // EXL2: scale words of (group, strip); GPTQ: zero words
     half gsc[8];            // GPTQ: fp16 scales of the lane's 8 columns
-    uint32_t zc[2][4];      // GPTQ: per-row zero constants (half2 bits)
     half smax;
     int cur_group;
+    int cur_bits;
 };
 
 __device__ __forceinline__ void acc_flush(WarpAcc& a, const QMatView& w, int g) {     // tot += scale(group, n) * grp
@@ -115,23 +122,30 @@ __device__ __forceinline__ void acc_flush(WarpAcc& a, const QMatView& w, int g) 
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int j = 4 * blk + 2 * sub + rr;
-                float s;
+                const int nib = (int)((a.sw[j] >> (4 * g)) & 15u);
+                float s, coff;
                 if (!w.is_gptq) {
-                    const int q = (int)((a.sw[j] >> (4 * g)) & 15u) + 1;
+                    const int q = nib + 1;
                     s = __half2float(__hmul(__int2half_rn(q * q), a.smax));     // fp16 scale, qdq_util.cuh:24-30
+                    coff = (a.cur_bits == 4) ? (float)(OFFSET4 + 8) : 0.f;      // offset form: A = 64 + q, zero point 8
                 } else {
                     s = __half2float(a.gsc[j]);
+                    coff = (float)(OFFSET4 + nib + 1);                          // zero + 1, q_gemm_kernel_gptq.cuh:169
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    a.tot[blk][sub][2 * rr + e] = fmaf(s, a.grp[blk][sub][2 * rr + e], a.tot[blk][sub][2 * rr + e]);
+                    const float v = fmaf(-coff, a.sacc[e], a.grp[blk][sub][2 * rr + e]);
+                    a.tot[blk][sub][2 * rr + e] = fmaf(s, v, a.tot[blk][sub][2 * rr + e]);
                     a.grp[blk][sub][2 * rr + e] = 0.f;
                 }
             }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a.sacc[e] = 0.f;
 }
 
-__device__ __forceinline__ void acc_enter_group(WarpAcc& a, const QMatView& w, int grp, int strip, int g) {
+__device__ __forceinline__ void acc_enter_group(WarpAcc& a, const QMatView& w, int grp, int strip, int g, int bits) {
     a.cur_group = grp;
+    a.cur_bits = bits;
     const int n_words = w.N >> 3;
     const uint32_t* src = (w.is_gptq ? w.qzeros : w.q_scale) + (size_t)grp * n_words + strip * 8;
 #pragma unroll
@@ -143,9 +157,6 @@ __device__ __forceinline__ void acc_enter_group(WarpAcc& a, const QMatView& w, i
         for (int j = 0; j < 8; ++j) {
             const int n = strip * STRIP_N + (j >> 2) * 32 + ((j >> 1) & 1) * 16 + (j & 1) * 8 + g;
             a.gsc[j] = (n < w.N) ? __ldg(w.gptq_scales + (size_t)grp * w.N + n) : __float2half(0.f);
-            const int z1 = (int)((a.sw[j] >> (4 * g)) & 15u) + 1;      // zero + 1, q_gemm_kernel_gptq.cuh:169
-            const half2 c2 = __half2half2(__int2half_rn(-(((j & 1) ? 64 : 1024) + z1)));
-            a.zc[j >> 2][j & 3] = *reinterpret_cast<const uint32_t*>(&c2);
         }
     }
 }
@@ -162,19 +173,24 @@ __device__ __forceinline__ void consume_run(WarpAcc& a, const QMatView& w, const
         const int d = d0 + i;
         if (a.cur_group < 0 || (d & gmask) == 0) {
             if (a.cur_group >= 0) acc_flush(a, w, g);
-            acc_enter_group(a, w, R.group_base + (d >> R.spg_log2), strip, g);
+            acc_enter_group(a, w, R.group_base + (d >> R.spg_log2), strip, g, BITS);
         }
         uint32_t B[4] = {0u, 0u, 0u, 0u};
         if (has_b) {
             const uint4 b4 = *reinterpret_cast<const uint4*>(bptr + i * (SLAB_K * 2));
             B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w;
         }
+        if constexpr (BITS == 4) {          // offset form: the all-ones row yields sum_k a[k] per token
+            const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};
+            mma16816(a.sacc, ones, B[0], B[1]);
+            mma16816(a.sacc, ones, B[2], B[3]);
+        }
         const uint8_t* sm = sp + i * slab_bytes(BITS);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
             uint32_t mw[8], ew[2], A[16];
             load_lane_words<BITS>(sm + blk * block_bytes(BITS), lane, mw, ew);
-            if constexpr (GPTQ) dequant_block_gptq(mw, a.zc[blk], A);
+            if constexpr (BITS == 4) dequant_block_4bit_offset(mw, A);
             else dequant_block_exl2<BITS>(mw, ew, A);
             mma_block(a.grp[blk], A, B);
         }
@@ -190,6 +206,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 
     griddep_launch_dependents();   // let the next kernel in the stream start prefetching its weights
     DBG_STAMP(0);
+    if (P.dbg && tid == 0) atomicMin(P.dbg + 6, gtimer());
 
     const uint32_t smem0 = smem_addr(smem);
     const uint32_t ring = smem0 + warp * RING_BYTES;
@@ -356,7 +373,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) a.tot[i][j][c] = 0.f, a.grp[i][j][c] = 0.f;
         a.cur_group = -1;
+        a.cur_bits = 0;
         a.smax = __float2half(0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a.sacc[e] = 0.f;
 
         const bool has_b = g < M;
         const uint8_t* bbase = act_s + (size_t)g * P.act_stride + t * 16;
@@ -490,6 +510,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
         DBG_STAMP(5);
         u += seg;
     }
+    if (P.dbg && tid == 0) atomicMax(P.dbg + 7, gtimer());
 }
 
 // ---- host launcher -----------------------------------------------------------------------------------------------
@@ -497,6 +518,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 int g_ctas_per_sm = 2;
 unsigned long long* g_dbg = nullptr;
 int g_dbg_cta = 0;
+int g_dbg_slot = 0;
 
 struct DeviceWorkspace {
     float* ws = nullptr;
@@ -557,11 +579,21 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     P.epilogue = epilogue;
     P.ws = dw->ws;
     P.counters = dw->counters;
-    P.dbg = g_dbg;
+    P.dbg = g_dbg ? g_dbg + 8 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
 
     const int sms = device_sm_count(device);
-    const int grid = (int)std::max(1ll, std::min((long long)sms * g_ctas_per_sm, units));
+    // Grid: when every strip can be cut into S equal K-ranges with strips * S <= resident slots, do exactly that
+    // (every CTA = one segment of one strip, no CTA pays the per-segment latency chain twice); otherwise plain
+    // stream-K over all slots.
+    const long long slots = (long long)sms * g_ctas_per_sm;
+    long long grid_ll = std::min(slots, units);
+    if (strips <= slots) {
+        int S = (int)(slots / strips);
+        while (S > 1 && (P.KS % S) != 0) --S;
+        grid_ll = (long long)strips * S;
+    }
+    const int grid = (int)std::max(1ll, grid_ll);
     EXL2B_REQUIRE((units + 1) * grid < (1ll << 31), "problem too large for 32-bit unit arithmetic");
     P.total_units = (int)units;
     const int seg_max = (int)std::min((long long)P.KS, (units + grid - 1) / grid);
@@ -635,5 +667,6 @@ extern "C" int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int 
     if (ctas_per_sm > 0) exl2b::g_ctas_per_sm = ctas_per_sm;
     exl2b::g_dbg = stamps;
     exl2b::g_dbg_cta = cta;
+    exl2b::g_dbg_slot = 0;
     return 0;
 }

@@ -149,7 +149,8 @@ int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, 
 int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_host, uint16_t* c_host, int m, exl2b_stream_t stream);
 
 /* Tuning / diagnostics hook (no reference counterpart): CTAs per SM of the GEMV grid (<= 0 keeps the current value)
- * and an optional device buffer of 8 uint64 that receives globaltimer phase stamps of CTA `cta` (NULL disables). */
+ * and an optional device buffer of 64 x 8 uint64 (one slot per launch, round robin): [0..5] globaltimer phase stamps of
+ * CTA `cta`, [6] earliest CTA start (pre-fill with ~0), [7] latest CTA end (NULL disables). */
 int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta);
 
 /* Stand-in for flash_attn_with_kvcache (third-party in the reference, attn.py:602-613): appends the q_len new K/V rows

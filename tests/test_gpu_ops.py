@@ -245,7 +245,8 @@ def test_q_mlp_block(rows):
     x = rng.normal(0, 1, size=(rows, hidden)).astype(np.float16)
     ta = torch.empty((rows, inter), dtype=torch.half, device=DEV)
     tb = torch.empty_like(ta)
-    h = ext_c.make_q_mlp(torch.from_numpy(norm_w).to(DEV), none_tensor, True, 1e-5, lg.q_handle, lu.q_handle, ld.q_handle,
+    nw = torch.from_numpy(norm_w).to(DEV)          # must outlive the handle (raw pointer, like the reference)
+    h = ext_c.make_q_mlp(nw, none_tensor, True, 1e-5, lg.q_handle, lu.q_handle, ld.q_handle,
                          none_tensor, ta, tb, none_tensor, 64, False, True, none_tensor, none_tensor, False, True)
     xt = torch.from_numpy(x).to(DEV)
     ext_c.q_mlp_forward_(h, xt)

@@ -111,15 +111,23 @@ def main():
                     ext_c.gemm_half_q_half(a, h, c, False)
 
             if args.phases:
-                stamps = torch.zeros((16,), dtype=torch.int64, device=DEV)
-                for cta in (0, 73, 147):
+                nl = min(len(handles), 12)
+                stamps = torch.zeros((64, 8), dtype=torch.int64, device=DEV)
+                for cta in (0, 100):
+                    stamps.zero_()
+                    stamps[:, 6] = 2**62
+                    run_new(); torch.cuda.synchronize()
                     ext_c.lib.exl2b_debug_set(0, stamps.data_ptr(), cta)
-                    run_new()
+                    for h in handles[:nl]:
+                        ext_c.gemm_half_q_half(a, h, c, False)
                     torch.cuda.synchronize()
+                    ext_c.lib.exl2b_debug_set(0, None, 0)
                     st = stamps.cpu().tolist()
-                    clk = [st[i] - st[0] for i in range(6)]
-                    print(json.dumps({"shape": name, "M": M, "cta": cta, "phase_clk[start,prefetch,wait,staged,consumed,done]": clk}), flush=True)
-                ext_c.lib.exl2b_debug_set(0, None, 0)
+                    t0 = st[0][6]
+                    for i in range(nl):
+                        r = st[i]
+                        print(json.dumps({"shape": name, "M": M, "cta": cta, "launch": i, "grid_start": r[6] - t0, "grid_end": r[7] - t0,
+                                          "cta[start,prefetched,wait_done,staged,consumed,done]": [x - t0 for x in r[:6]]}), flush=True)
             t_eager = time_loop(run_new, 5)
             # graph-captured cycle (no host launch overhead)
             g = torch.cuda.CUDAGraph()
