@@ -1,0 +1,596 @@
+// tcgen05 dequant-GEMM: packed EXL2 / GPTQ weights -> fp16 in TENSOR MEMORY -> tcgen05.mma against the activations.
+// Serves batch-1 decode through batched rows with ONE kernel (LAYOUT_TC matrices); replaces gemm_half_q_half_kernel
+// (exllamav2_ext/cuda/q_gemm_kernel.cuh:140-565), gemm_half_q_half_gptq_kernel (q_gemm_kernel_gptq.cuh:61-246) and the
+// reconstruct + cublasHgemm detour for M > 32 (cuda/q_gemm.cu:233-266).
+//
+// Why tensor memory even for M = 1: measured on B200 (tools/ubench/pipes.cu, profiles/), the legacy mma.sync path
+// tops out near 0.45 HMMA.16816/clk/SM and a dequant+mma.sync loop at ~52 4-bit weights/clk/SM -- the whole SM is
+// busy just keeping up with HBM (49 weights/clk/SM at 6.5 TB/s).  With UMMA the weights are the M = 128 operand:
+//     D[128 weight columns x 16 tokens] += A[128 x 16 k] (TMEM) * B[16 k x 16 tokens] (shared memory)
+// one instruction covers 2048 weights in 8 clk, and the only per-weight work left on the CUDA cores is the unpack
+// (3 SHF + 4 LOP3 per 8 four-bit weights) plus one tcgen05.st per 1024 weights.
+//
+// Mapping (layout.h, LAYOUT_TC): strip = 128 output columns = the 128 TMEM lanes; a thread IS a weight column n.
+//   * 256 threads = 2 warpgroups (WG).  Warp w of a WG owns TMEM lane quadrant w and streams ITS 32-column block of the
+//     strip with cp.async.bulk (TMA 1-D) into a private 3-stage ring, exactly one quantisation group (<= 128 k) per
+//     stage.  WG0 takes even groups, WG1 odd groups: two independent software pipelines sharing the tensor core.
+//   * per group: unpack 32 k per LDS.128 into 16 half2 registers = 16 TMEM columns of the thread's row
+//     (tcgen05.st.32x32b.x16), barrier inside the WG, one thread issues 2 MMAs per 32 k into the WG's accumulator
+//     D[wg] (and, for the 4-bit offset form, 2 more against an all-ones A tile to obtain sum_k a[k] per token),
+//     tcgen05.commit -> mbarrier.  One group later the WG reads D back (tcgen05.ld), applies the group's fp16 scale
+//     in fp32 -- a per-THREAD scalar, since a thread is a column -- and adds into its running totals.
+//   * activations: the 128 threads of a WG write the group's [128 k x 16 token] B tile (no-swizzle K-major core
+//     matrices) into shared memory, gathered through q_perm, RMSNorm folded in.
+//   * epilogue: WG0 + WG1 totals are combined through shared memory; split-K across CTAs and the bias / residual /
+//     silu(gate)*up epilogues are the ones of the mma.sync kernel (fixed-order, deterministic).
+#include <algorithm>
+#include <mutex>
+
+#include "dequant.cuh"
+#include "gemv.cuh"
+
+namespace exl2b {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_WARPS = 8;
+constexpr int TC_STAGE_BYTES = 4096;              // one group (<= 4 slabs) of one 32-column block, any bit width
+constexpr int TC_STAGES = 3;
+constexpr int TC_RING = TC_STAGE_BYTES * TC_STAGES;
+constexpr int TC_SMEM_RINGS = TC_WARPS * TC_RING;                 // 96 KB
+constexpr int TC_NTOK = 16;                       // UMMA N (tokens per pass are padded to 16)
+constexpr int TC_B_BYTES = 128 * TC_NTOK * 2;     // one WG's B tile: 128 k x 16 tokens fp16 = 4 KB
+constexpr int TC_SMEM_B = 2 * TC_B_BYTES;
+constexpr int TC_SMEM_BARS = (TC_WARPS * TC_STAGES + 2) * 8;
+constexpr int TC_SMEM_MISC = 128;                 // tmem base, rstd[16], flag
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_COL_ONES = 0;                    // 8 columns: all-ones A tile (K = 16)
+constexpr int TC_COL_WG = 8;                      // per WG: A 64 cols | D 16 | D2 16
+constexpr int TC_COLS_PER_WG = 96;
+constexpr int TC_RED_FLOATS = GEMV_MTOK * 128;    // workspace floats per (strip, contributor)
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8_same(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v), "r"(v), "r"(v),
+                 "r"(v), "r"(v), "r"(v), "r"(v), "r"(v)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    v = __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// D[tmem] (+)= A[tmem] * B[smem desc];  M = 128, N = 16, K = 16, fp16 in, fp32 accumulate
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): F32 accumulate, F16 x F16, K-major A and B,
+// N = 16, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_NTOK >> 3) << 17) | ((128u >> 4) << 24);
+// shared-memory descriptor of a no-swizzle K-major operand: core matrix = 8 rows x 16 bytes, contiguous (128 B);
+// LBO = byte distance between core matrices adjacent in K, SBO = between core matrices adjacent in N (tokens)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_byte_addr) {
+    constexpr uint64_t LBO = (TC_NTOK / 8) * 128, SBO = 128;
+    return (uint64_t)((smem_byte_addr >> 4) & 0x3FFF) | ((LBO >> 4) << 16) | ((SBO >> 4) << 32) | (1ull << 46);
+}
+// byte offset of element (k, tok) inside a WG's B tile
+__device__ __forceinline__ int b_off(int k, int tok) { return ((k >> 3) * (TC_NTOK / 8) + (tok >> 3)) * 128 + (tok & 7) * 16 + (k & 7) * 2; }
+
+__device__ __forceinline__ int tc_cta_of_unit(unsigned x, unsigned G, unsigned U) { return (int)(((x + 1u) * G - 1u) / U); }
+__device__ __forceinline__ int tc_region_of(const QMatView& w, int ks) {
+    int r = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_REGIONS; ++i)
+        if (i < w.num_regions && ks >= w.reg[i].ks_begin) r = i;
+    return r;
+}
+__device__ __forceinline__ int tc_region_end(const QMatView& w, int r) { return (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS; }
+// first slab of the group that contains slab ks (ks == KS maps to KS)
+__device__ __forceinline__ int tc_group_start(const QMatView& w, int ks) {
+    if (ks >= w.KS) return w.KS;
+    const QRegion& R = w.reg[tc_region_of(w, ks)];
+    return R.ks_begin + (((ks - R.ks_begin) >> R.spg_log2) << R.spg_log2);
+}
+
+__device__ __forceinline__ half tc_silu_h(half x) {
+    half e = hexp(__hneg(x));
+    half r = hrcp(__hadd(__float2half(1.0f), e));
+    return __hmul(x, r);
+}
+__device__ __forceinline__ half tc_gelu_h(half x) {
+    float xf = __half2float(x);
+    const float c = 0.797884560803f;
+    float t = c * (xf + 0.044715f * xf * xf * xf), th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+    xf = 0.5f * xf * (1.0 + th);
+    return __float2half_rn(xf);
+}
+
+template <int BITS>
+__device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uint32_t* mw, uint32_t* ew) {
+    constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
+    if constexpr (Pm == 8) {
+        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16), b = *reinterpret_cast<const uint4*>(base + 512 + lane * 16);
+        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
+    } else if constexpr (Pm == 4) {
+        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16);
+        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w;
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(base + lane * 8);
+        mw[0] = a.x; mw[1] = a.y;
+    }
+    if constexpr (Pe == 1) {
+        ew[0] = *reinterpret_cast<const uint32_t*>(base + 128 * Pm + lane * 4);
+    } else if constexpr (Pe == 2) {
+        const uint2 a = *reinterpret_cast<const uint2*>(base + 128 * Pm + lane * 8);
+        ew[0] = a.x; ew[1] = a.y;
+    }
+}
+
+// unpack `nslab` slabs of this warp's block (contiguous at sp) into the WG's A buffer: 16 TMEM columns per slab
+template <int BITS>
+__device__ __forceinline__ void tc_dequant_group(const uint8_t* sp, int nslab, int lane, uint32_t a_taddr) {
+#pragma unroll 1
+    for (int i = 0; i < nslab; ++i) {
+        uint32_t mw[8], ew[2], A[16];
+        tc_load_words<BITS>(sp + i * block_bytes(BITS), lane, mw, ew);
+        if constexpr (BITS == 4) dequant_block_4bit_offset(mw, A);
+        else dequant_block_exl2<BITS>(mw, ew, A);
+        tmem_st16(a_taddr + i * 16, A);
+    }
+}
+
+template <int MT>   // MT = 1 (decode) or 8 tokens per pass
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemvParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = warp >> 2, wq = warp & 3, tidw = tid & 127;       // warpgroup, TMEM lane quadrant, thread = weight column
+
+    griddep_launch_dependents();
+
+    uint8_t* ring_p = smem + warp * TC_RING;
+    const uint32_t smem0 = smem_addr(smem);
+    const uint32_t ring = smem0 + warp * TC_RING;
+    uint8_t* bs_p = smem + TC_SMEM_RINGS + wg * TC_B_BYTES;
+    const uint32_t bs = smem0 + TC_SMEM_RINGS + wg * TC_B_BYTES;
+    const uint32_t bars = smem0 + TC_SMEM_RINGS + TC_SMEM_B + warp * TC_STAGES * 8;
+    const uint32_t bar_mma = smem0 + TC_SMEM_RINGS + TC_SMEM_B + TC_WARPS * TC_STAGES * 8 + wg * 8;
+    uint8_t* misc = smem + TC_SMEM_RINGS + TC_SMEM_B + TC_SMEM_BARS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
+    float* rstd_s = reinterpret_cast<float*>(misc + 16);          // [8]
+    int* flag_s = reinterpret_cast<int*>(misc + 64);
+    float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [MT][128] WG1 totals / norm partial sums
+    const int M = P.M, KS = P.KS;
+
+    // ---- one-time setup: barriers, TMEM, zeroed B tiles, all-ones A tile ----
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+        if (wq == 0) mbar_init(bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
+    for (int i = tid; i < TC_SMEM_B / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem + TC_SMEM_RINGS)[i] = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const uint32_t t_ones = tmem_base + TC_COL_ONES;
+    const uint32_t t_a = tmem_base + TC_COL_WG + wg * TC_COLS_PER_WG, t_d = t_a + 64, t_d2 = t_a + 80;
+    if (wg == 0) {
+        tmem_st8_same(t_ones + lane_sel, 0x3C003C00u);       // half2(1, 1)
+        tmem_wait_st();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const unsigned U = (unsigned)P.total_units, G = gridDim.x;
+    const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
+
+    uint32_t phases = 0, mma_phase = 0;
+    bool first_seg = true;
+    int u = u0;
+    while (u < u1) {
+        int mi = 0;
+        while (mi + 1 < P.num_mats && u >= P.mat[mi + 1].unit_begin) ++mi;
+        const GemvMat& mt = P.mat[mi];
+        const QMatView& w = mt.w;
+        const int local = u - mt.unit_begin;
+        const int strip = local / KS, ks_a = local - strip * KS;
+        const int seg = min(KS - ks_a, u1 - u);
+        // snap the slab range to group boundaries (every CTA applies the same rule, so ranges still tile the strip)
+        const int ks0 = tc_group_start(w, ks_a), ks1 = tc_group_start(w, ks_a + seg);
+        const int n_col = strip * 128 + tidw;                                  // this thread's output column
+        const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
+
+        // group iterator of this WG: groups ks0.., WG takes every other one
+        auto group_len = [&](int ks) {          // slabs in the group starting at ks
+            const int r = tc_region_of(w, ks);
+            return min(1 << w.reg[r].spg_log2, tc_region_end(w, r) - ks);
+        };
+        auto next_group = [&](int ks) { return ks + group_len(ks); };
+        int g_first = ks0;
+        if (wg == 1 && g_first < ks1) g_first = next_group(g_first);
+
+        // ---- producer: this warp's block stream, one group per stage ----
+        int fetch_ks = g_first, fstage = 0, cstage = 0;
+        auto issue = [&]() {
+            const int r = tc_region_of(w, fetch_ks);
+            const QRegion& R = w.reg[r];
+            const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - fetch_ks);
+            const uint32_t bytes = (uint32_t)ns * block_bytes(R.bits);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
+                bulk_copy_g2s(ring + fstage * TC_STAGE_BYTES, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * block_bytes(R.bits),
+                              bytes, bars + 8 * fstage);
+            }
+            int nk = fetch_ks + ns;                       // skip the other WG's group
+            if (nk < ks1) nk = next_group(nk);
+            fetch_ks = nk;
+            fstage = (fstage + 1 == TC_STAGES) ? 0 : fstage + 1;
+        };
+#pragma unroll 1
+        for (int s = 0; s < TC_STAGES && fetch_ks < ks1; ++s) issue();
+
+        if (first_seg) {
+            griddep_wait();
+            if (P.norm_w) {      // RMSNorm statistics per token (cuda/rms_norm.cu:55-111)
+                const int K = w.K;
+                for (int m = warp; m < M; m += TC_WARPS) {
+                    const half* xr = mt.x + (size_t)m * mt.ldx;
+                    float sum = 0.f;
+                    for (int k = lane * 8; k < K; k += 256) {
+                        const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
+                        const half2* h2 = reinterpret_cast<const half2*>(&v4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
+                            float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
+                            sum = fmaf(f0, f0, sum);
+                            sum = fmaf(f1, f1, sum);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
+                }
+                __syncthreads();
+            }
+            first_seg = false;
+        }
+
+        // ---- the WG pipeline over its groups ----
+        float tot[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tot[m] = 0.f;
+        bool pending = false;
+        float pend_scale = 0.f, pend_coff = 0.f;
+        bool pend_offset = false;
+
+        auto drain = [&]() {       // read back the previous group's accumulator, apply its scale
+            mbar_wait(bar_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            float d[MT], d2[MT];
+            if constexpr (MT == 1) {
+                tmem_ld1(t_d + lane_sel, d[0]);
+                if (pend_offset) tmem_ld1(t_d2 + lane_sel, d2[0]); else d2[0] = 0.f;
+            } else {
+                tmem_ld8(t_d + lane_sel, d);
+                if (pend_offset) tmem_ld8(t_d2 + lane_sel, d2);
+                else {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) d2[m] = 0.f;
+                }
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, fmaf(-pend_coff, d2[m], d[m]), tot[m]);
+            tc_fence_before();
+        };
+
+        int gk = g_first;
+        while (gk < ks1) {
+            const int r = tc_region_of(w, gk);
+            const QRegion& R = w.reg[r];
+            const int bits = R.bits;
+            const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - gk);
+            const int grp = R.group_base + ((gk - R.ks_begin) >> R.spg_log2);
+
+            // (a) this group's scale / zero for my column and my activation rows: requested now, used later
+            float sc = 0.f, coff = 0.f;
+            const bool offset_form = (bits == 4);
+            if (n_col < w.N) {
+                if (!w.is_gptq) {
+                    const uint32_t word = __ldg(w.q_scale + (size_t)grp * (w.N >> 3) + (n_col >> 3));
+                    const int q = (int)((word >> ((n_col & 7) * 4)) & 15u) + 1;
+                    sc = __half2float(__hmul(__int2half_rn(q * q), __ldg(w.q_scale_max + grp)));    // qdq_util.cuh:24-30
+                    coff = offset_form ? (float)(OFFSET4 + 8) : 0.f;
+                } else {
+                    const uint32_t word = __ldg(w.qzeros + (size_t)grp * (w.N >> 3) + (n_col >> 3));
+                    sc = __half2float(__ldg(w.gptq_scales + (size_t)grp * w.N + n_col));
+                    coff = (float)(OFFSET4 + (int)((word >> ((n_col & 7) * 4)) & 15u) + 1);       // zero + 1
+                }
+            }
+            half av[MT];
+            {
+                const int kp = gk * SLAB_K + tidw;
+                const bool live = tidw < ns * SLAB_K;
+                const int src = live ? (w.perm ? (int)__ldg(w.perm + kp) : kp) : 0;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    half v = __float2half(0.f);
+                    if (live && m < M) {
+                        v = mt.x[(size_t)m * mt.ldx + src];
+                        if (P.norm_w) {
+                            float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
+                            v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
+                        }
+                    }
+                    av[m] = v;
+                }
+            }
+
+            // (b) previous group of this WG: MMAs done -> D readable, A buffer and B tile free
+            if (pending) drain();
+
+            // (c) B tile: row k = tidw, tokens 0..MT-1 (the other token columns stay zero)
+#pragma unroll
+            for (int m = 0; m < MT; ++m) *reinterpret_cast<half*>(bs_p + b_off(tidw, m)) = av[m];
+
+            // (d) unpack my block's slabs of this group into TMEM
+            mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
+            phases ^= 1u << cstage;
+            const uint8_t* sp = ring_p + cstage * TC_STAGE_BYTES;
+            const uint32_t a_dst = t_a + lane_sel;
+            switch (bits) {
+                case 4: tc_dequant_group<4>(sp, ns, lane, a_dst); break;
+                case 5: tc_dequant_group<5>(sp, ns, lane, a_dst); break;
+                case 3: tc_dequant_group<3>(sp, ns, lane, a_dst); break;
+                case 6: tc_dequant_group<6>(sp, ns, lane, a_dst); break;
+                case 2: tc_dequant_group<2>(sp, ns, lane, a_dst); break;
+                default: tc_dequant_group<8>(sp, ns, lane, a_dst); break;
+            }
+            tmem_wait_st();
+            fence_proxy_async_smem();
+            tc_fence_before();
+            bar_sync(1 + wg, 128);
+
+            // (e) one thread feeds the tensor core
+            if (tidw == 0) {
+                tc_fence_after();
+                for (int j = 0; j < 2 * ns; ++j) {
+                    const uint64_t bd = make_b_desc(bs + j * 2 * (TC_NTOK / 8) * 128);
+                    umma_ts(t_d, t_a + j * 8, bd, TC_IDESC, j > 0 ? 1u : 0u);
+                    if (offset_form) umma_ts(t_d2, t_ones, bd, TC_IDESC, j > 0 ? 1u : 0u);
+                }
+                umma_commit(bar_mma);
+            }
+            pending = true;
+            pend_scale = sc;
+            pend_coff = coff;
+            pend_offset = offset_form;
+
+            // (f) refill my weight stage, advance to this WG's next group
+            cstage = (cstage + 1 == TC_STAGES) ? 0 : cstage + 1;
+            if (fetch_ks < ks1) issue();
+            int nk = gk + ns;
+            if (nk < ks1) nk = next_group(nk);
+            gk = nk;
+        }
+        if (pending) drain();
+
+        // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
+        __syncthreads();
+        if (wg == 1) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) comb_s[m * 128 + tidw] = tot[m];
+        }
+        __syncthreads();
+
+        const int gs = mt.strip_begin + strip;
+        const unsigned sb = (unsigned)mt.unit_begin + (unsigned)strip * KS;
+        const int first_cta = tc_cta_of_unit(sb, G, U), last_cta = tc_cta_of_unit(sb + KS - 1, G, U);
+        const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
+        const bool paired = P.epilogue != EPI_STORE;
+        auto epilogue_store = [&](int m, float v) {
+            if (n_col < w.N && m < M) {
+                if (w.bias) v += __half2float(w.bias[n_col]);
+                half* cp = mt.c + (size_t)m * mt.ldc + n_col;
+                if (!mt.clear) v += __half2float(*cp);
+                *cp = __float2half_rn(v);
+            }
+        };
+        if (wg == 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) tot[m] += comb_s[m * 128 + tidw];
+        }
+        if (nc == 1 && !paired) {
+            if (wg == 0) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) epilogue_store(m, tot[m]);
+            }
+        } else {
+            float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * TC_RED_FLOATS;
+            if (wg == 0) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) __stcg(wsp + m * 128 + tidw, tot[m]);
+            }
+            __threadfence();
+            __syncthreads();
+            int expected = nc, cidx = gs;
+            if (paired) {
+                const GemvMat& other = P.mat[1 - mi];
+                const unsigned ob = (unsigned)other.unit_begin + (unsigned)strip * KS;
+                expected += tc_cta_of_unit(ob + KS - 1, G, U) - tc_cta_of_unit(ob, G, U) + 1;
+                cidx = P.mat[0].strip_begin + strip;
+            }
+            if (tid == 0) {
+                const unsigned int old = atomicAdd(P.counters + cidx, 1u);
+                *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (*flag_s) {
+                __threadfence();
+                if (wg == 0) {
+                    if (!paired) {
+                        const float* base = P.ws + (size_t)gs * P.maxc * TC_RED_FLOATS;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            float v = 0.f;
+                            for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            epilogue_store(m, v);
+                        }
+                    } else {
+                        const GemvMat& mg = P.mat[0];
+                        const GemvMat& mu = P.mat[1];
+                        const unsigned gb = (unsigned)mg.unit_begin + (unsigned)strip * KS;
+                        const unsigned ub = (unsigned)mu.unit_begin + (unsigned)strip * KS;
+                        const int ncg = tc_cta_of_unit(gb + KS - 1, G, U) - tc_cta_of_unit(gb, G, U) + 1;
+                        const int ncu = tc_cta_of_unit(ub + KS - 1, G, U) - tc_cta_of_unit(ub, G, U) + 1;
+                        const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
+                        const float* bu = P.ws + (size_t)(mu.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            float vg = 0.f, vu = 0.f;
+                            for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            if (n_col < mg.w.N && m < M) {
+                                if (mg.w.bias) vg += __half2float(mg.w.bias[n_col]);
+                                if (mu.w.bias) vu += __half2float(mu.w.bias[n_col]);
+                                const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);   // q_mlp.cu:187-196 roundings
+                                const half act = (P.epilogue == EPI_GELU_MUL) ? tc_gelu_h(hg) : tc_silu_h(hg);
+                                mg.c[(size_t)m * mg.ldc + n_col] = __hmul(act, hu);
+                            }
+                        }
+                    }
+                }
+                if (tid == 0) P.counters[cidx] = 0u;
+            }
+        }
+        __syncthreads();
+        u += seg;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---- host launcher -----------------------------------------------------------------------------------------------------
+
+int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters);
+
+int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue) {
+    EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
+    if (M <= 0) return 0;
+    float* ws = nullptr;
+    unsigned int* counters = nullptr;
+    size_t ws_bytes = 0;
+    int n_counters = 0;
+    int rc = gemv_workspace(device, &ws, &counters, &ws_bytes, &n_counters);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    if (!attr_set[device]) {
+        EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[device] = true;
+    }
+
+    GemvParams P = {};
+    P.num_mats = nm;
+    P.KS = mats[0].w.KS;
+    long long units = 0;
+    int strips = 0;
+    for (int i = 0; i < nm; ++i) {
+        EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_TC, "matrix is not in the tcgen05 layout");
+        EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
+        P.mat[i] = mats[i];
+        P.mat[i].unit_begin = (int)units;
+        P.mat[i].strip_begin = strips;
+        units += (long long)mats[i].w.strips * P.KS;
+        strips += mats[i].w.strips;
+    }
+    if (norm_w) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
+    if (epilogue != EPI_STORE) EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
+    P.norm_w = norm_w;
+    P.norm_eps = norm_eps;
+    P.epilogue = epilogue;
+    P.ws = ws;
+    P.counters = counters;
+
+    const int sms = device_sm_count(device);
+    const long long slots = sms;                      // one CTA per SM: leaves TMEM / smem for the next kernel's CTA (PDL)
+    long long grid_ll = std::min(slots, units);
+    if (strips <= slots) {
+        int S = (int)(slots / strips);
+        while (S > 1 && (P.KS % S) != 0) --S;
+        grid_ll = (long long)strips * S;
+    }
+    const int grid = (int)std::max(1ll, grid_ll);
+    EXL2B_REQUIRE((units + 1) * grid < (1ll << 31), "problem too large for 32-bit unit arithmetic");
+    P.total_units = (int)units;
+    P.maxc = (int)(((long long)P.KS * grid) / units) + 2;
+    EXL2B_REQUIRE(strips <= n_counters, "too many strips for the counter array");
+    EXL2B_REQUIRE((size_t)strips * P.maxc * TC_RED_FLOATS * sizeof(float) <= ws_bytes, "split-K workspace too small");
+
+    const int fixed = TC_SMEM_RINGS + TC_SMEM_B + TC_SMEM_BARS + TC_SMEM_MISC;
+    for (int m0 = 0; m0 < M; m0 += GEMV_MTOK) {
+        P.M = std::min(GEMV_MTOK, M - m0);
+        for (int i = 0; i < nm; ++i) {
+            P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
+            P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
+        }
+        if (P.M == 1) {
+            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), (size_t)fixed + 1 * 128 * 4, stream, P));
+        } else {
+            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<8>, dim3(grid), dim3(TC_THREADS), (size_t)fixed + 8 * 128 * 4, stream, P));
+        }
+    }
+    return 0;
+}
+
+}  // namespace exl2b

@@ -549,11 +549,25 @@ static int ensure_workspace(int device, DeviceWorkspace** out) {
     return 0;
 }
 
+int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters) {
+    DeviceWorkspace* dw = nullptr;
+    int rc = ensure_workspace(device, &dw);
+    if (rc) return rc;
+    *ws = dw->ws;
+    *counters = dw->counters;
+    *ws_bytes = dw->ws_bytes;
+    *n_counters = dw->n_counters;
+    return 0;
+}
+
+int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue);
+
 int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps,
                 int epilogue) {
     EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
     EXL2B_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
     if (M <= 0) return 0;
+    if (mats[0].w.layout == LAYOUT_TC) return gemm_tc_launch(device, stream, mats, nm, M, norm_w, norm_eps, epilogue);
     DeviceWorkspace* dw = nullptr;
     int rc = ensure_workspace(device, &dw);
     if (rc) return rc;
@@ -565,6 +579,7 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     int strips = 0;
     for (int i = 0; i < nm; ++i) {
         EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
+        EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_MMA, "matrix is not in the mma.sync layout");
         P.mat[i] = mats[i];
         P.mat[i].unit_begin = (int)units;
         P.mat[i].strip_begin = strips;

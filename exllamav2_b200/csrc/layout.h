@@ -107,6 +107,19 @@ EXL2B_HD constexpr int index_of(int n_local, int k_local) {
     return p * 2 + e;
 }
 
+// ---- second lane mapping ("TC" layout, used by the tcgen05 kernel) ----------------------------------------------------
+// strip = 128 columns = 4 blocks; each block's slabs form their own contiguous stream ([strip][blk][slab]), lane l of a
+// block owns column n = l and all 32 k of the slab: value i <-> k_local = i, pair p = i/2 = (k, k+1).  After unpacking,
+// register p of lane l is half2(W[k=2p][n], W[2p+1][n]) -- exactly one 32-bit TMEM column of row n of the UMMA A
+// operand (M = 128 weight columns on the TMEM lanes, K along TMEM columns), written with tcgen05.st.32x32b.
+constexpr int LAYOUT_MMA = 0;   // mma.sync fragment layout above (strip 64)
+constexpr int LAYOUT_TC = 1;    // tcgen05 / TMEM row layout (strip 128)
+EXL2B_HD constexpr int strip_n(int layout) { return layout == LAYOUT_TC ? 128 : 64; }
+EXL2B_HD constexpr int strip_blocks(int layout) { return layout == LAYOUT_TC ? 4 : 2; }
+EXL2B_HD constexpr ValuePos value_pos_l(int layout, int lane, int i) {
+    return layout == LAYOUT_TC ? ValuePos{lane, i} : value_pos(lane, i);
+}
+
 // Compose the lane's plane words from its 32 integer values q[i] (0 <= q < 2^bits).
 // out_main: main_words(bits) words, out_extra: extra_words(bits) words.
 EXL2B_HD void compose_lane_words(int bits, const uint32_t* q, uint32_t* out_main, uint32_t* out_extra) {

@@ -43,9 +43,16 @@ struct GroupInfo {   // per EXL2 group (device array)
     int row0;         // first stored k row
 };
 
+// byte offset of block `blk` of slab (tab.x) of `strip` for either layout
+__device__ __forceinline__ size_t block_offset(int layout, int strip, int blk, uint32_t tab_x, int bits, uint32_t strip_bytes,
+                                               uint32_t blk_stream_bytes) {
+    return layout == LAYOUT_TC ? (size_t)strip * strip_bytes + (size_t)blk * blk_stream_bytes + tab_x
+                               : (size_t)strip * strip_bytes + tab_x + (size_t)blk * block_bytes(bits);
+}
+
 __global__ void repack_exl2_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int N, int KS,
                                    const uint2* __restrict__ slab_tab, const GroupInfo* __restrict__ ginfo,
-                                   uint32_t strip_bytes) {
+                                   uint32_t strip_bytes, uint32_t blk_stream_bytes, int layout) {
     const int ks = blockIdx.x, strip = blockIdx.y;
     const int blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint2 tab = slab_tab[ks];
@@ -54,8 +61,8 @@ __global__ void repack_exl2_kernel(const uint32_t* __restrict__ src, uint32_t* _
     uint32_t vals[32];
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
-        const ValuePos vp = value_pos(lane, i);
-        const int n = strip * STRIP_N + blk * BLOCK_N + vp.n_local;
+        const ValuePos vp = value_pos_l(layout, lane, i);
+        const int n = strip * strip_n(layout) + blk * BLOCK_N + vp.n_local;
         const int r = ks * SLAB_K + vp.k_local - gi.row0;
         const int bitpos = r * bits;
         const int word = gi.first_qrow + (bitpos >> 5), sh = bitpos & 31;
@@ -69,21 +76,21 @@ __global__ void repack_exl2_kernel(const uint32_t* __restrict__ src, uint32_t* _
     }
     uint32_t mw[8], ew[4];
     compose_lane_words(bits, vals, mw, ew);
-    uint32_t* bp = dst + ((size_t)strip * strip_bytes + tab.x) / 4 + (size_t)blk * (32 * bits);
+    uint32_t* bp = dst + block_offset(layout, strip, blk, tab.x, bits, strip_bytes, blk_stream_bytes) / 4;
     const int Pm = plane_main(bits), Pe = plane_extra(bits);
     for (int w = 0; w < Pm; ++w) bp[main_word_index(bits, lane, w)] = mw[w];
     for (int w = 0; w < Pe; ++w) bp[extra_word_index(bits, lane, w)] = ew[w];
 }
 
 __global__ void repack_gptq_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int N, int KS,
-                                   const uint16_t* __restrict__ perm, uint32_t strip_bytes) {
+                                   const uint16_t* __restrict__ perm, uint32_t strip_bytes, uint32_t blk_stream_bytes, int layout) {
     const int ks = blockIdx.x, strip = blockIdx.y;
     const int blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t vals[32];
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
-        const ValuePos vp = value_pos(lane, i);
-        const int n = strip * STRIP_N + blk * BLOCK_N + vp.n_local;
+        const ValuePos vp = value_pos_l(layout, lane, i);
+        const int n = strip * strip_n(layout) + blk * BLOCK_N + vp.n_local;
         const int kp = ks * SLAB_K + vp.k_local;
         const int row = perm ? (int)perm[kp] : kp;    // stored row k' <- checkpoint row perm[k'] (make_sequential)
         uint32_t v = 0;
@@ -92,7 +99,8 @@ __global__ void repack_gptq_kernel(const uint32_t* __restrict__ src, uint32_t* _
     }
     uint32_t mw[8], ew[4];
     compose_lane_words(4, vals, mw, ew);
-    uint32_t* bp = dst + ((size_t)strip * strip_bytes + (size_t)ks * slab_bytes(4)) / 4 + (size_t)blk * (32 * 4);
+    const uint32_t tab_x = (uint32_t)ks * (layout == LAYOUT_TC ? block_bytes(4) : slab_bytes(4));
+    uint32_t* bp = dst + block_offset(layout, strip, blk, tab_x, 4, strip_bytes, blk_stream_bytes) / 4;
     for (int w = 0; w < 4; ++w) bp[main_word_index(4, lane, w)] = mw[w];
 }
 
@@ -121,19 +129,17 @@ __device__ void reconstruct_block_exl2(const QMatView& v, const uint32_t* bp, in
     uint32_t mw[8], ew[4], A[16];
     load_block_words<BITS>(bp, lane, mw, ew);
     dequant_block_exl2<BITS>(mw, ew, A);
-    const int g = lane >> 2;
     const half smax = v.q_scale_max[group];
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
-        const int rr = p & 1, sub = (p >> 3) & 1;
-        const int n = n0 + sub * 16 + rr * 8 + g;
+        const int n = n0 + value_pos_l(v.layout, lane, p * 2).n_local;
         if (n >= v.N) continue;
         const uint32_t word = v.q_scale[(size_t)group * (v.N / 8) + (n >> 3)];
         const half s = exl2_scale_h((word >> ((n & 7) * 4)) & 15u, smax);
         const half2 w2 = __hmul2(*reinterpret_cast<const half2*>(&A[p]), __half2half2(s));
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int kp = k0 + value_pos(lane, p * 2 + e).k_local;
+            const int kp = k0 + value_pos_l(v.layout, lane, p * 2 + e).k_local;
             const int row = v.perm ? (int)v.perm[kp] : kp;
             out[(size_t)row * v.N + n] = e ? __high2half(w2) : __low2half(w2);
         }
@@ -145,8 +151,8 @@ __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restr
     const int blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint2 tab = v.slab_tab[ks];
     const int bits = (tab.y >> 16) & 0xF, group = tab.y & 0xFFFF;
-    const uint32_t* bp = v.packed + ((size_t)strip * v.strip_bytes + tab.x) / 4 + (size_t)blk * (32 * bits);
-    const int n0 = strip * STRIP_N + blk * BLOCK_N, k0 = ks * SLAB_K;
+    const uint32_t* bp = v.packed + block_offset(v.layout, strip, blk, tab.x, bits, v.strip_bytes, v.blk_stream_bytes) / 4;
+    const int n0 = strip * strip_n(v.layout) + blk * BLOCK_N, k0 = ks * SLAB_K;
     if (!v.is_gptq) {
         switch (bits) {
             case 2: reconstruct_block_exl2<2>(v, bp, lane, group, n0, k0, out); break;
@@ -157,33 +163,23 @@ __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restr
             case 8: reconstruct_block_exl2<8>(v, bp, lane, group, n0, k0, out); break;
         }
     } else {
-        uint32_t mw[8], ew[4], A[16], zc[4];
+        uint32_t mw[8], ew[4];
         load_block_words<4>(bp, lane, mw, ew);
-        const int g = lane >> 2;
-        half sc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + (j >> 1) * 16 + (j & 1) * 8 + g;
-            int z1 = 1;
-            sc[j] = __float2half(0.f);
-            if (n < v.N) {
-                z1 = (int)((v.qzeros[(size_t)group * (v.N / 8) + (n >> 3)] >> ((n & 7) * 4)) & 15u) + 1;
-                sc[j] = v.gptq_scales[(size_t)group * v.N + n];
-            }
-            const half c = __int2half_rn(-(((j & 1) ? 64 : 1024) + z1));
-            const half2 c2 = __half2half2(c);
-            zc[j] = *reinterpret_cast<const uint32_t*>(&c2);
-        }
-        dequant_block_gptq(mw, zc, A);
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
-            const int rr = p & 1, sub = (p >> 3) & 1;
-            const int n = n0 + sub * 16 + rr * 8 + g;
+            const int n = n0 + value_pos_l(v.layout, lane, p * 2).n_local;
             if (n >= v.N) continue;
-            const half2 w2 = __hmul2(__half2half2(sc[sub * 2 + rr]), *reinterpret_cast<const half2*>(&A[p]));
+            const int z1 = (int)((v.qzeros[(size_t)group * (v.N / 8) + (n >> 3)] >> ((n & 7) * 4)) & 15u) + 1;
+            const half sc = v.gptq_scales[(size_t)group * v.N + n];
+            const int jm = pair_slot(4, p);
+            const uint32_t x = mw[pair_word(4, p)] >> field_sh(4, jm);
+            const uint32_t tm = and_or(x, field_mask(4, jm), field_magic(4, jm));
+            const half2 c2 = __half2half2(__int2half_rn(-((1 << field_exp(4, jm)) + z1)));
+            const uint32_t qz = h2add_bits(tm, *reinterpret_cast<const uint32_t*>(&c2));       // q - (zero + 1), exact
+            const half2 w2 = __hmul2(__half2half2(sc), *reinterpret_cast<const half2*>(&qz));
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int kp = k0 + value_pos(lane, p * 2 + e).k_local;
+                const int kp = k0 + value_pos_l(v.layout, lane, p * 2 + e).k_local;
                 const int row = v.perm ? (int)v.perm[kp] : kp;
                 out[(size_t)row * v.N + n] = e ? __high2half(w2) : __low2half(w2);
             }
@@ -194,7 +190,7 @@ __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restr
 // ---- host side ---------------------------------------------------------------------------------------------------
 
 static int build_tables_exl2(const exl2b_qmatrix_desc* d, const uint16_t* hg, std::vector<uint2>& tab,
-                             std::vector<GroupInfo>& ginfo, uint32_t& bits_mask, uint32_t& strip_bytes) {
+                             std::vector<GroupInfo>& ginfo, uint32_t& bits_mask, uint32_t& strip_bytes, int layout) {
     const int G = d->groups, K = d->height;
     ginfo.resize(G);
     int row = 0;
@@ -222,9 +218,9 @@ static int build_tables_exl2(const exl2b_qmatrix_desc* d, const uint16_t* hg, st
         while (gi + 1 < G && ks * SLAB_K >= ginfo[gi + 1].row0) gi++;
         tab[ks].x = off;
         tab[ks].y = (uint32_t)gi | ((uint32_t)ginfo[gi].bits << 16);
-        off += slab_bytes(ginfo[gi].bits);
+        off += (layout == LAYOUT_TC) ? block_bytes(ginfo[gi].bits) : slab_bytes(ginfo[gi].bits);
     }
-    strip_bytes = off;
+    strip_bytes = off;      // MMA: bytes of a strip;  TC: bytes of one block stream (caller multiplies by 4)
     return 0;
 }
 
@@ -314,10 +310,15 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
     QMatrix* m = new QMatrix();
     m->device = d->device;
     QMatView& v = m->v;
+    static const int default_layout = [] {
+        const char* e = getenv("EXL2B_LAYOUT");
+        return (e && e[0] == 'm') ? LAYOUT_MMA : LAYOUT_TC;
+    }();
+    v.layout = default_layout;
     v.K = d->height;
     v.N = d->width;
     v.KS = v.K / SLAB_K;
-    v.strips = (v.N + STRIP_N - 1) / STRIP_N;
+    v.strips = (v.N + strip_n(v.layout) - 1) / strip_n(v.layout);
     v.groups = d->groups;
     v.is_gptq = is_gptq ? 1 : 0;
     v.q_scale = d->q_scale;
@@ -337,14 +338,16 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
             set_error("copying q_groups failed: %s", cudaGetErrorString(cudaGetLastError()));
             return fail(-1);
         }
-        int rc = build_tables_exl2(d, hg.data(), m->slab_tab_host, ginfo, m->bits_mask, v.strip_bytes);
+        int rc = build_tables_exl2(d, hg.data(), m->slab_tab_host, ginfo, m->bits_mask, v.strip_bytes, v.layout);
         if (rc) return fail(rc);
+        v.blk_stream_bytes = v.strip_bytes;
+        if (v.layout == LAYOUT_TC) v.strip_bytes *= 4;
         std::vector<int> group_rows(d->groups);
         for (int i = 0; i < d->groups; ++i) group_rows[i] = (i + 1 < d->groups ? ginfo[i + 1].row0 : v.K) - ginfo[i].row0;
         rc = build_regions(v, m->slab_tab_host, group_rows);
         if (rc) return fail(rc);
         fill_left_same(m->slab_tab_host);
-        const uint64_t expect_rows = (uint64_t)v.strip_bytes / 256;   // sum over slabs of bits == packed rows
+        const uint64_t expect_rows = (uint64_t)v.strip_bytes / (v.layout == LAYOUT_TC ? 512 : 256);   // sum over slabs of bits == packed rows
         if (d->q_weight_rows && (uint64_t)d->q_weight_rows != expect_rows) {
             set_error("q_weight has %d rows, groups imply %llu", d->q_weight_rows, (unsigned long long)expect_rows);
             return fail(-2);
@@ -356,10 +359,11 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
         m->bits_mask = 1u << 4;
         m->slab_tab_host.resize(v.KS);
         for (int ks = 0; ks < v.KS; ++ks) {
-            m->slab_tab_host[ks].x = (uint32_t)ks * slab_bytes(4);
+            m->slab_tab_host[ks].x = (uint32_t)ks * (v.layout == LAYOUT_TC ? block_bytes(4) : slab_bytes(4));
             m->slab_tab_host[ks].y = (uint32_t)(ks * SLAB_K / gptq_gs) | (4u << 16) | ((uint32_t)std::min(v.KS - ks, 4095) << 20);
         }
-        v.strip_bytes = (uint32_t)v.KS * slab_bytes(4);
+        v.blk_stream_bytes = (uint32_t)v.KS * block_bytes(4);
+        v.strip_bytes = (uint32_t)v.KS * block_bytes(4) * strip_blocks(v.layout);
         {
             int lg = 0;
             while ((SLAB_K << lg) < gptq_gs) ++lg;
@@ -410,15 +414,17 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
         set_error("CUDA out of memory");        // same message as the reference (ext_qmatrix.cpp:108)
         return fail(-3);
     }
-    dim3 grid(v.KS, v.strips), block(32 * STRIP_BLOCKS);
+    dim3 grid(v.KS, v.strips), block(32 * strip_blocks(v.layout));
     if (!is_gptq)
-        repack_exl2_kernel<<<grid, block, 0, stream>>>(d->q_weight, tmp, v.N, v.KS, v.slab_tab, d_ginfo, v.strip_bytes);
+        repack_exl2_kernel<<<grid, block, 0, stream>>>(d->q_weight, tmp, v.N, v.KS, v.slab_tab, d_ginfo, v.strip_bytes,
+                                                       v.blk_stream_bytes, v.layout);
     else
-        repack_gptq_kernel<<<grid, block, 0, stream>>>(d->q_weight, tmp, v.N, v.KS, v.perm, v.strip_bytes);
+        repack_gptq_kernel<<<grid, block, 0, stream>>>(d->q_weight, tmp, v.N, v.KS, v.perm, v.strip_bytes, v.blk_stream_bytes,
+                                                       v.layout);
     g_launch_count++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
-        if (v.N % STRIP_N == 0) {
+        if (v.N % strip_n(v.layout) == 0) {
             e = cudaMemcpyAsync(d->q_weight, tmp, m->packed_bytes, cudaMemcpyDeviceToDevice, stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
             cudaFree(tmp);
@@ -465,7 +471,7 @@ extern "C" int exl2b_reconstruct(exl2b_qmatrix_t h, uint16_t* out, exl2b_stream_
     EXL2B_REQUIRE(m && out, "null argument");
     EXL2B_CUDA(cudaSetDevice(m->device));
     int gs = 0;
-    dim3 grid(m->v.KS, m->v.strips), block(32 * STRIP_BLOCKS);
+    dim3 grid(m->v.KS, m->v.strips), block(32 * strip_blocks(m->v.layout));
     reconstruct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(m->v, gs, (half*)out);
     g_launch_count++;
     EXL2B_CUDA(cudaGetLastError());

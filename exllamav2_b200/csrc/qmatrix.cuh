@@ -20,7 +20,7 @@ constexpr int MAX_REGIONS = 6;
 // Device-side view handed to kernels by value.
 struct QMatView {
     const uint32_t* packed;       // [strips][strip_bytes]  private layout
-    const uint2* slab_tab;        // [KS]  .x = byte offset of the slab inside a strip,
+    const uint2* slab_tab;        // [KS]  .x = byte offset of the slab inside a strip (MMA) / inside a block stream (TC),
                                   //       .y = group | bits << 16 | slabs-left-with-same-bits << 20
     const uint32_t* q_scale;      // EXL2 int32[G, N/8]   (checkpoint layout, read directly)
     const half* q_scale_max;      // EXL2 fp16[G]
@@ -28,7 +28,9 @@ struct QMatView {
     const half* gptq_scales;      // GPTQ fp16[G, N]
     const uint16_t* perm;         // [K] or NULL
     const half* bias;             // [N] or NULL
-    uint32_t strip_bytes;
+    uint32_t strip_bytes;         // bytes of one strip (all blocks, all K)
+    uint32_t blk_stream_bytes;    // LAYOUT_TC: bytes of one block's stream over K (strip_bytes / 4)
+    int layout;                   // LAYOUT_MMA (strip 64, [strip][slab][blk]) or LAYOUT_TC (strip 128, [strip][blk][slab])
     int K, N, KS, strips, groups;
     int is_gptq;
     int num_regions;
