@@ -207,6 +207,16 @@ def run_ours(args, rank, world):
     dec.cache.cache_seqlens.copy_(saved)
     dec.ids.copy_(prompt[:, -1:])
 
+    if os.environ.get("EXL2B_PROFILE"):
+        # ncu --profile-from-start off: capture exactly two eager decode steps (launch list / --set full)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(2):
+            step_with_argmax()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_steps": 2}))
+        return
     W, K = max(3, args.warmup), args.steps
     assert args.prompt_len + 2 * (W + K) + 8 < dec.cache.max_seq_len
     for _ in range(W):

@@ -139,4 +139,23 @@ EXL2B_HD void dequant_block_4bit_offset(const uint32_t* mw, uint32_t* A) {
     }
 }
 
+// Two-offset form: no shift for slots 0/1, one shift for slots 2/3 -> 4 LOP3 + 1 SHF per 8 weights, all on the ALU pipe
+// (LOP3 / SHF issue at half rate on sm_100, so the ALU pipe is what bounds the unpack; measured tools/ubench).
+//   even pair slots: (x & 0x000f000f) | 0x6400 = 1024 + q      odd pair slots: (x & 0x00f000f0) | 0x5400 = 64 + q
+// The per-slot offset (+ the zero point) is removed by one extra MMA against a constant "offset tile".
+EXL2B_HD constexpr int offset2_of_pair(int p) { return (p & 1) ? 64 : 1024; }
+EXL2B_HD void dequant_block_4bit_offset2(const uint32_t* mw, uint32_t* A) {
+    const uint32_t m0 = 0x000f000fu, g0 = 0x64006400u, m1 = 0x00f000f0u, g1 = 0x54005400u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = mw[w], y = x >> 8;
+        A[w * 4 + 0] = and_or(x, m0, g0);
+        A[w * 4 + 1] = and_or(x, m1, g1);
+        A[w * 4 + 2] = and_or(y, m0, g0);
+        A[w * 4 + 3] = and_or(y, m1, g1);
+    }
+}
+
 }  // namespace exl2b

@@ -33,18 +33,14 @@ namespace exl2b {
 
 constexpr int TC_THREADS = 256;
 constexpr int TC_WARPS = 8;
-constexpr int TC_STAGE_BYTES = 4096;              // one group (<= 4 slabs) of one 32-column block, any bit width
-constexpr int TC_STAGES = 3;
-constexpr int TC_RING = TC_STAGE_BYTES * TC_STAGES;
-constexpr int TC_SMEM_RINGS = TC_WARPS * TC_RING;                 // 96 KB
-constexpr int TC_NTOK = 16;                       // UMMA N (tokens per pass are padded to 16)
-constexpr int TC_B_BYTES = 128 * TC_NTOK * 2;     // one WG's B tile: 128 k x 16 tokens fp16 = 4 KB
-constexpr int TC_SMEM_B = 2 * TC_B_BYTES;
-constexpr int TC_SMEM_BARS = (TC_WARPS * TC_STAGES + 2) * 8;
-constexpr int TC_SMEM_MISC = 128;                 // tmem base, rstd[16], flag
+constexpr int TC_STAGES = 4;                      // stage = one group (<= 4 slabs) of one 32-column block; size set per launch
+constexpr int TC_NTOK = 16;                       // UMMA N; tokens 8..15 alias tokens 0..7 (SBO = 0), only 8 are real
+constexpr int TC_SMEM_BARS = (TC_WARPS * TC_STAGES + 4) * 8;
+constexpr int TC_SMEM_MISC = 128;                 // tmem base, rstd[8], flag
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_COL_ONES = 0;                    // 8 columns: all-ones A tile (K = 16)
-constexpr int TC_COL_WG = 8;                      // per WG: A 64 cols | D 16 | D2 16
+constexpr int TC_COL_OFFS = 8;                    // 8 columns: two-offset tile of the EXL2 4-bit unpack (+ zero point)
+constexpr int TC_COL_WG = 16;                     // per WG: A 64 cols | D 16 | D2 16
 constexpr int TC_COLS_PER_WG = 96;
 constexpr int TC_RED_FLOATS = GEMV_MTOK * 128;    // workspace floats per (strip, contributor)
 
@@ -67,12 +63,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+    // no "memory" clobber: the store touches tensor memory only, so the compiler may overlap the next slab's
+    // shared-memory loads and unpack with it (ordering against the MMA is tcgen05.wait::st + fence + barrier)
 }
-__device__ __forceinline__ void tmem_st8_same(uint32_t taddr, uint32_t v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v), "r"(v), "r"(v),
-                 "r"(v), "r"(v), "r"(v), "r"(v), "r"(v)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
@@ -100,6 +97,17 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
+// one lane of a converged warp (the tcgen05.mma / commit issuer); returns non-zero in the elected lane
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync _|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -109,12 +117,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_NTOK >> 3) << 17) | ((128u >> 4) << 24);
 // shared-memory descriptor of a no-swizzle K-major operand: core matrix = 8 rows x 16 bytes, contiguous (128 B);
 // LBO = byte distance between core matrices adjacent in K, SBO = between core matrices adjacent in N (tokens)
+// The staged activations hold ONE 8-token core matrix per 8 k (128 B); the descriptor's token-group stride is 0, so
+// UMMA columns 8..15 re-read tokens 0..7 (their D columns are never looked at).
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_byte_addr) {
-    constexpr uint64_t LBO = (TC_NTOK / 8) * 128, SBO = 128;
+    constexpr uint64_t LBO = 128, SBO = 0;
     return (uint64_t)((smem_byte_addr >> 4) & 0x3FFF) | ((LBO >> 4) << 16) | ((SBO >> 4) << 32) | (1ull << 46);
 }
-// byte offset of element (k, tok) inside a WG's B tile
-__device__ __forceinline__ int b_off(int k, int tok) { return ((k >> 3) * (TC_NTOK / 8) + (tok >> 3)) * 128 + (tok & 7) * 16 + (k & 7) * 2; }
+// byte offset of element (k, tok < 8) in the staged activations (k relative to the segment start)
+__device__ __forceinline__ int b_off(int k, int tok) { return (k >> 3) * 128 + tok * 16 + (k & 7) * 2; }
 
 __device__ __forceinline__ int tc_cta_of_unit(unsigned x, unsigned G, unsigned U) { return (int)(((x + 1u) * G - 1u) / U); }
 __device__ __forceinline__ int tc_region_of(const QMatView& w, int ks) {
@@ -146,6 +156,13 @@ __device__ __forceinline__ half tc_gelu_h(half x) {
     return __float2half_rn(xf);
 }
 
+__device__ __forceinline__ unsigned long long tc_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && tid == 0) P.dbg[i] = tc_gtimer(); if ((i) == 0 && tid == 0) atomicMin(P.dbg + 6, tc_gtimer()); } } while (0)
+
 template <int BITS>
 __device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uint32_t* mw, uint32_t* ew) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
@@ -168,61 +185,139 @@ __device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uin
 }
 
 // unpack `nslab` slabs of this warp's block (contiguous at sp) into the WG's A buffer: 16 TMEM columns per slab
-template <int BITS>
+template <int BITS, int MODE>    // MODE 0: exact (q - zp), 1: 4-bit two-offset form, 2: 4-bit uniform-offset form (GPTQ)
+__device__ __forceinline__ void tc_dequant_slab(const uint8_t* sp, int i, int lane, uint32_t a_taddr) {
+    uint32_t mw[8], ew[2], A[16];
+    tc_load_words<BITS>(sp + i * block_bytes(BITS), lane, mw, ew);
+    if constexpr (MODE == 1) dequant_block_4bit_offset2(mw, A);
+    else if constexpr (MODE == 2) dequant_block_4bit_offset(mw, A);
+    else dequant_block_exl2<BITS>(mw, ew, A);
+    tmem_st16(a_taddr + i * 16, A);
+}
+template <int BITS, int MODE>
 __device__ __forceinline__ void tc_dequant_group(const uint8_t* sp, int nslab, int lane, uint32_t a_taddr) {
+    if (nslab == 4) {            // the common case (128-row groups): straight-line code, slabs interleave freely
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc_dequant_slab<BITS, MODE>(sp, i, lane, a_taddr);
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < nslab; ++i) {
-        uint32_t mw[8], ew[2], A[16];
-        tc_load_words<BITS>(sp + i * block_bytes(BITS), lane, mw, ew);
-        if constexpr (BITS == 4) dequant_block_4bit_offset(mw, A);
-        else dequant_block_exl2<BITS>(mw, ew, A);
-        tmem_st16(a_taddr + i * 16, A);
+        for (int i = 0; i < nslab; ++i) tc_dequant_slab<BITS, MODE>(sp, i, lane, a_taddr);
+    }
+}
+
+// ---- activation prep: RMSNorm + q_perm gather + UMMA core-matrix layout, once per launch ------------------------------
+// xp[mat][k'/8][tok 0..7][k'%8] = half(x[tok][perm_mat[k']] * w[perm] * rstd[tok])   (rows tok >= M are zero)
+// One CTA per token slot (8 CTAs).  The GEMV CTAs then fetch their k-range with ONE bulk copy -- no per-CTA gather.
+struct PrepParams {
+    const half* x;          // [M][ldx]
+    int ldx, M, K, num_mats;
+    const half* norm_w;     // or NULL
+    float norm_eps;
+    const uint16_t* perm[GEMV_MAX_MATS];
+    half* xp[GEMV_MAX_MATS];
+};
+__global__ void __launch_bounds__(1024) tc_prep_kernel(const __grid_constant__ PrepParams P) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int tok = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float part[32];
+    float rstd = 1.f;
+    const bool live = tok < P.M;
+    const half* xr = P.x + (size_t)tok * P.ldx;
+    if (live && P.norm_w) {            // cuda/rms_norm.cu:55-111: clamp, fp32 sum of squares, rsqrt(mean + eps)
+        float sum = 0.f;
+        for (int k = tid * 8; k < P.K; k += 1024 * 8) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
+            const half2* h2 = reinterpret_cast<const half2*>(&v4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
+                float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
+                sum = fmaf(f0, f0, sum);
+                sum = fmaf(f1, f1, sum);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) part[warp] = sum;
+        __syncthreads();
+        float t = (lane < 32) ? part[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        rstd = rsqrtf(t * (1.0f / (float)P.K) + P.norm_eps);
+    }
+    for (int mi = 0; mi < P.num_mats; ++mi) {
+        const uint16_t* perm = P.perm[mi];
+        half* dst = P.xp[mi];
+        for (int kp = tid; kp < P.K; kp += 1024) {
+            half v = __float2half(0.f);
+            if (live) {
+                const int src = perm ? (int)__ldg(perm + kp) : kp;
+                v = xr[src];
+                if (P.norm_w) {
+                    float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
+                    v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd);
+                }
+            }
+            dst[(size_t)(kp >> 3) * 64 + tok * 8 + (kp & 7)] = v;
+        }
     }
 }
 
 template <int MT>   // MT = 1 (decode) or 8 tokens per pass
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);         // provably warp-uniform (UMMA operands live in uniform registers)
     const int wg = warp >> 2, wq = warp & 3, tidw = tid & 127;       // warpgroup, TMEM lane quadrant, thread = weight column
 
     griddep_launch_dependents();
+    TC_STAMP(0);
 
-    uint8_t* ring_p = smem + warp * TC_RING;
+    // shared memory: [barriers][misc][WG1 totals] | [activations = UMMA B operand] | [8 weight rings]
     const uint32_t smem0 = smem_addr(smem);
-    const uint32_t ring = smem0 + warp * TC_RING;
-    uint8_t* bs_p = smem + TC_SMEM_RINGS + wg * TC_B_BYTES;
-    const uint32_t bs = smem0 + TC_SMEM_RINGS + wg * TC_B_BYTES;
-    const uint32_t bars = smem0 + TC_SMEM_RINGS + TC_SMEM_B + warp * TC_STAGES * 8;
-    const uint32_t bar_mma = smem0 + TC_SMEM_RINGS + TC_SMEM_B + TC_WARPS * TC_STAGES * 8 + wg * 8;
-    uint8_t* misc = smem + TC_SMEM_RINGS + TC_SMEM_B + TC_SMEM_BARS;
+    const int stage_bytes = P.tc_stage_bytes;
+    const uint32_t bars = smem0 + warp * TC_STAGES * 8;
+    const uint32_t bar_mma = smem0 + TC_WARPS * TC_STAGES * 8 + wg * 8;
+    const uint32_t bar_act = smem0 + TC_WARPS * TC_STAGES * 8 + 16;
+    uint8_t* misc = smem + TC_SMEM_BARS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
-    float* rstd_s = reinterpret_cast<float*>(misc + 16);          // [8]
     int* flag_s = reinterpret_cast<int*>(misc + 64);
-    float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [MT][128] WG1 totals / norm partial sums
+    float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [MT][128]
+    const uint32_t act_a = smem0 + P.tc_act_off;
+    const int ring_off = P.tc_act_off + P.tc_act_bytes;
+    uint8_t* ring_p = smem + ring_off + warp * TC_STAGES * stage_bytes;
+    const uint32_t ring = smem0 + ring_off + warp * TC_STAGES * stage_bytes;
     const int M = P.M, KS = P.KS;
 
-    // ---- one-time setup: barriers, TMEM, zeroed B tiles, all-ones A tile ----
+    // ---- one-time setup: barriers, TMEM, constant A tiles ----
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < TC_STAGES; ++s) mbar_init(bars + 8 * s, 1);
         if (wq == 0) mbar_init(bar_mma, 1);
+        if (warp == 0) mbar_init(bar_act, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
-    for (int i = tid; i < TC_SMEM_B / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem + TC_SMEM_RINGS)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const uint32_t t_ones = tmem_base + TC_COL_ONES;
+    const uint32_t t_ones = tmem_base + TC_COL_ONES, t_offs = tmem_base + TC_COL_OFFS;
     const uint32_t t_a = tmem_base + TC_COL_WG + wg * TC_COLS_PER_WG, t_d = t_a + 64, t_d2 = t_a + 80;
     if (wg == 0) {
-        tmem_st8_same(t_ones + lane_sel, 0x3C003C00u);       // half2(1, 1)
+        // all-ones tile (GPTQ: sum_k a[k]) and the two-offset tile of the EXL2 4-bit unpack incl. its zero point:
+        // k-pairs alternate (1024 + 8), (64 + 8)  -> D2 = sum_k a[k] * (offset_k + 8)
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0x3C003C00u;
+        tmem_st8(t_ones + lane_sel, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = h2_const_int(offset2_of_pair(j) + 8);
+        tmem_st8(t_offs + lane_sel, r);
         tmem_wait_st();
     }
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -230,8 +325,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const unsigned U = (unsigned)P.total_units, G = gridDim.x;
     const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
 
-    uint32_t phases = 0, mma_phase = 0;
-    bool first_seg = true;
+    uint32_t phases = 0, mma_phase = 0, act_phase = 0;
+    bool waited = false;
     int u = u0;
     while (u < u1) {
         int mi = 0;
@@ -246,81 +341,66 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int n_col = strip * 128 + tidw;                                  // this thread's output column
         const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
 
-        // group iterator of this WG: groups ks0.., WG takes every other one
         auto group_len = [&](int ks) {          // slabs in the group starting at ks
             const int r = tc_region_of(w, ks);
             return min(1 << w.reg[r].spg_log2, tc_region_end(w, r) - ks);
         };
-        auto next_group = [&](int ks) { return ks + group_len(ks); };
         int g_first = ks0;
-        if (wg == 1 && g_first < ks1) g_first = next_group(g_first);
+        if (wg == 1 && g_first < ks1) g_first += group_len(g_first);
 
-        // ---- producer: this warp's block stream, one group per stage ----
+        // ---- producer: this warp's block stream, one group per stage (weights never depend on a previous kernel) ----
         int fetch_ks = g_first, fstage = 0, cstage = 0;
         auto issue = [&]() {
             const int r = tc_region_of(w, fetch_ks);
             const QRegion& R = w.reg[r];
             const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - fetch_ks);
             const uint32_t bytes = (uint32_t)ns * block_bytes(R.bits);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
-                bulk_copy_g2s(ring + fstage * TC_STAGE_BYTES, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * block_bytes(R.bits),
+                bulk_copy_g2s(ring + fstage * stage_bytes, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * block_bytes(R.bits),
                               bytes, bars + 8 * fstage);
             }
             int nk = fetch_ks + ns;                       // skip the other WG's group
-            if (nk < ks1) nk = next_group(nk);
+            if (nk < ks1) nk += group_len(nk);
             fetch_ks = nk;
             fstage = (fstage + 1 == TC_STAGES) ? 0 : fstage + 1;
         };
 #pragma unroll 1
         for (int s = 0; s < TC_STAGES && fetch_ks < ks1; ++s) issue();
-
-        if (first_seg) {
-            griddep_wait();
-            if (P.norm_w) {      // RMSNorm statistics per token (cuda/rms_norm.cu:55-111)
-                const int K = w.K;
-                for (int m = warp; m < M; m += TC_WARPS) {
-                    const half* xr = mt.x + (size_t)m * mt.ldx;
-                    float sum = 0.f;
-                    for (int k = lane * 8; k < K; k += 256) {
-                        const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
-                        const half2* h2 = reinterpret_cast<const half2*>(&v4);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
-                            float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
-                            sum = fmaf(f0, f0, sum);
-                            sum = fmaf(f1, f1, sum);
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
-                }
-                __syncthreads();
-            }
-            first_seg = false;
-        }
+        TC_STAMP(1);
 
         // ---- the WG pipeline over its groups ----
         float tot[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) tot[m] = 0.f;
-        bool pending = false;
-        float pend_scale = 0.f, pend_coff = 0.f;
-        bool pend_offset = false;
+        bool pending = false, act_issued = false;
+        int pend_mode = 0;               // 0: exact unpack, 1: EXL2 4-bit two-offset (D - D2), 2: GPTQ (D - (64 + z + 1) * S)
+        uint32_t pend_word = 0;          // raw q_scale / qzeros word of the pending group (decoded only when consumed:
+        half pend_h = __float2half(0.f); //   the SM issues in order, so touching a load result early stalls the warp)
 
         auto drain = [&]() {       // read back the previous group's accumulator, apply its scale
             mbar_wait(bar_mma, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
+            float pend_scale = 0.f, pend_coff = 0.f;
+            if (n_col < w.N) {
+                const int nib = (int)((pend_word >> ((n_col & 7) * 4)) & 15u);
+                if (!w.is_gptq) {
+                    pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), pend_h));    // qdq_util.cuh:24-30
+                    pend_coff = pend_mode == 1 ? 1.f : 0.f;
+                } else {
+                    pend_scale = __half2float(pend_h);
+                    pend_coff = (float)(OFFSET4 + nib + 1);                                              // zero + 1
+                }
+            }
             float d[MT], d2[MT];
             if constexpr (MT == 1) {
                 tmem_ld1(t_d + lane_sel, d[0]);
-                if (pend_offset) tmem_ld1(t_d2 + lane_sel, d2[0]); else d2[0] = 0.f;
+                d2[0] = 0.f;
+                if (pend_mode) tmem_ld1(t_d2 + lane_sel, d2[0]);
             } else {
                 tmem_ld8(t_d + lane_sel, d);
-                if (pend_offset) tmem_ld8(t_d2 + lane_sel, d2);
+                if (pend_mode) tmem_ld8(t_d2 + lane_sel, d2);
                 else {
 #pragma unroll
                     for (int m = 0; m < MT; ++m) d2[m] = 0.f;
@@ -333,95 +413,118 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         };
 
         int gk = g_first;
+        int gi_dbg = 0;
+#define TC_GSTAMP(j) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0 && gi_dbg < 3) P.dbg[8 + gi_dbg * 6 + (j)] = tc_gtimer(); } while (0)
         while (gk < ks1) {
+            TC_GSTAMP(0);
             const int r = tc_region_of(w, gk);
             const QRegion& R = w.reg[r];
             const int bits = R.bits;
             const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - gk);
             const int grp = R.group_base + ((gk - R.ks_begin) >> R.spg_log2);
 
-            // (a) this group's scale / zero for my column and my activation rows: requested now, used later
-            float sc = 0.f, coff = 0.f;
-            const bool offset_form = (bits == 4);
+            // (a) this group's scale / zero for my column: requested now, decoded when the group is drained
+            const int mode = (bits == 4) ? (w.is_gptq ? 2 : 1) : 0;
+            uint32_t cur_word = 0;
+            half cur_h = __float2half(0.f);
             if (n_col < w.N) {
                 if (!w.is_gptq) {
-                    const uint32_t word = __ldg(w.q_scale + (size_t)grp * (w.N >> 3) + (n_col >> 3));
-                    const int q = (int)((word >> ((n_col & 7) * 4)) & 15u) + 1;
-                    sc = __half2float(__hmul(__int2half_rn(q * q), __ldg(w.q_scale_max + grp)));    // qdq_util.cuh:24-30
-                    coff = offset_form ? (float)(OFFSET4 + 8) : 0.f;
+                    cur_word = __ldg(w.q_scale + (size_t)grp * (w.N >> 3) + (n_col >> 3));
+                    cur_h = __ldg(w.q_scale_max + grp);
                 } else {
-                    const uint32_t word = __ldg(w.qzeros + (size_t)grp * (w.N >> 3) + (n_col >> 3));
-                    sc = __half2float(__ldg(w.gptq_scales + (size_t)grp * w.N + n_col));
-                    coff = (float)(OFFSET4 + (int)((word >> ((n_col & 7) * 4)) & 15u) + 1);       // zero + 1
-                }
-            }
-            half av[MT];
-            {
-                const int kp = gk * SLAB_K + tidw;
-                const bool live = tidw < ns * SLAB_K;
-                const int src = live ? (w.perm ? (int)__ldg(w.perm + kp) : kp) : 0;
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    half v = __float2half(0.f);
-                    if (live && m < M) {
-                        v = mt.x[(size_t)m * mt.ldx + src];
-                        if (P.norm_w) {
-                            float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
-                            v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
-                        }
-                    }
-                    av[m] = v;
+                    cur_word = __ldg(w.qzeros + (size_t)grp * (w.N >> 3) + (n_col >> 3));
+                    cur_h = __ldg(w.gptq_scales + (size_t)grp * w.N + n_col);
                 }
             }
 
-            // (b) previous group of this WG: MMAs done -> D readable, A buffer and B tile free
+            // (b) previous group of this WG: MMAs done -> D readable, A buffer free
             if (pending) drain();
+            TC_GSTAMP(1);
 
-            // (c) B tile: row k = tidw, tokens 0..MT-1 (the other token columns stay zero)
-#pragma unroll
-            for (int m = 0; m < MT; ++m) *reinterpret_cast<half*>(bs_p + b_off(tidw, m)) = av[m];
-
-            // (d) unpack my block's slabs of this group into TMEM
+            // (c) unpack my block's slabs of this group into TMEM
             mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
             phases ^= 1u << cstage;
-            const uint8_t* sp = ring_p + cstage * TC_STAGE_BYTES;
+            TC_GSTAMP(2);
+            const uint8_t* sp = ring_p + cstage * stage_bytes;
             const uint32_t a_dst = t_a + lane_sel;
             switch (bits) {
-                case 4: tc_dequant_group<4>(sp, ns, lane, a_dst); break;
-                case 5: tc_dequant_group<5>(sp, ns, lane, a_dst); break;
-                case 3: tc_dequant_group<3>(sp, ns, lane, a_dst); break;
-                case 6: tc_dequant_group<6>(sp, ns, lane, a_dst); break;
-                case 2: tc_dequant_group<2>(sp, ns, lane, a_dst); break;
-                default: tc_dequant_group<8>(sp, ns, lane, a_dst); break;
+                case 4:
+                    if (w.is_gptq) tc_dequant_group<4, 2>(sp, ns, lane, a_dst);
+                    else tc_dequant_group<4, 1>(sp, ns, lane, a_dst);
+                    break;
+                case 5: tc_dequant_group<5, 0>(sp, ns, lane, a_dst); break;
+                case 3: tc_dequant_group<3, 0>(sp, ns, lane, a_dst); break;
+                case 6: tc_dequant_group<6, 0>(sp, ns, lane, a_dst); break;
+                case 2: tc_dequant_group<2, 0>(sp, ns, lane, a_dst); break;
+                default: tc_dequant_group<8, 0>(sp, ns, lane, a_dst); break;
             }
+            TC_GSTAMP(3);
             tmem_wait_st();
-            fence_proxy_async_smem();
+
+            // everything above depended only on the weights; from here on we need the previous kernel's output
+            if (!waited) {
+                griddep_wait();
+                waited = true;
+                TC_STAMP(2);
+            }
+            if (!act_issued) {           // the segment's activations (UMMA layout, written by tc_prep_kernel): one bulk copy
+                act_issued = true;
+                if (warp == 0 && elect_one()) {
+                    const uint32_t bytes = (uint32_t)(ks1 - ks0) * SLAB_K * 16;
+                    mbar_arrive_expect_tx(bar_act, bytes);
+                    bulk_copy_g2s(act_a, reinterpret_cast<const uint8_t*>(mt.xp) + (size_t)ks0 * SLAB_K * 16, bytes, bar_act);
+                }
+                mbar_wait(bar_act, act_phase);
+                TC_STAMP(3);
+            }
             tc_fence_before();
             bar_sync(1 + wg, 128);
+            TC_GSTAMP(4);
 
-            // (e) one thread feeds the tensor core
-            if (tidw == 0) {
+            // (d) one elected lane of the WG's first warp feeds the tensor core: 2 MMAs (K = 16) per slab
+            if (wq == 0) {
                 tc_fence_after();
-                for (int j = 0; j < 2 * ns; ++j) {
-                    const uint64_t bd = make_b_desc(bs + j * 2 * (TC_NTOK / 8) * 128);
-                    umma_ts(t_d, t_a + j * 8, bd, TC_IDESC, j > 0 ? 1u : 0u);
-                    if (offset_form) umma_ts(t_d2, t_ones, bd, TC_IDESC, j > 0 ? 1u : 0u);
+                const uint64_t bd0 = make_b_desc(act_a + (uint32_t)((gk - ks0) * SLAB_K / 8) * 128);
+                const uint32_t t_c = mode == 1 ? t_offs : t_ones;
+                if (elect_one()) {
+                    // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
+                    if (ns == 4) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            umma_ts(t_d, t_a + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
+                            if (mode) umma_ts(t_d2, t_c, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
+                        }
+                    } else {
+                        for (int j = 0; j < 2 * ns; ++j) {
+                            umma_ts(t_d, t_a + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
+                            if (mode) umma_ts(t_d2, t_c, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar_mma);
                 }
-                umma_commit(bar_mma);
+                __syncwarp();
             }
+            TC_GSTAMP(5);
+            ++gi_dbg;
             pending = true;
-            pend_scale = sc;
-            pend_coff = coff;
-            pend_offset = offset_form;
+            pend_word = cur_word;
+            pend_h = cur_h;
+            pend_mode = mode;
 
-            // (f) refill my weight stage, advance to this WG's next group
+            // (e) refill my weight stage, advance to this WG's next group
             cstage = (cstage + 1 == TC_STAGES) ? 0 : cstage + 1;
             if (fetch_ks < ks1) issue();
             int nk = gk + ns;
-            if (nk < ks1) nk = next_group(nk);
+            if (nk < ks1) nk += group_len(nk);
             gk = nk;
         }
         if (pending) drain();
+        if (ks0 < ks1) act_phase ^= 1u;      // this activation barrier completed one phase (uniform across threads)
+        if (!waited) {                   // a CTA whose snapped range is empty still takes part in the fix-up below
+            griddep_wait();
+            waited = true;
+        }
+        TC_STAMP(4);
 
         // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
         __syncthreads();
@@ -512,17 +615,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             }
         }
         __syncthreads();
+        TC_STAMP(5);
         u += seg;
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (P.dbg && tid == 0) atomicMax(P.dbg + 7, tc_gtimer());
 }
 
 // ---- host launcher -----------------------------------------------------------------------------------------------------
 
 int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters);
+
+static half* g_xp_scratch[64] = {nullptr};
+constexpr size_t TC_XP_BYTES_PER_MAT = (size_t)65536 * 16;      // K <= 65536, 16 B per k (8 token slots)
 
 int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue) {
     EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
@@ -537,6 +645,7 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     if (!attr_set[device]) {
         EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaMalloc(&g_xp_scratch[device], TC_XP_BYTES_PER_MAT * GEMV_MAX_MATS));
         attr_set[device] = true;
     }
 
@@ -548,9 +657,11 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     for (int i = 0; i < nm; ++i) {
         EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_TC, "matrix is not in the tcgen05 layout");
         EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
+        EXL2B_REQUIRE(mats[i].x == mats[0].x && mats[i].ldx == mats[0].ldx, "fused matrices must share their input");
         P.mat[i] = mats[i];
         P.mat[i].unit_begin = (int)units;
         P.mat[i].strip_begin = strips;
+        P.mat[i].xp = g_xp_scratch[device] + (size_t)i * (TC_XP_BYTES_PER_MAT / sizeof(half));
         units += (long long)mats[i].w.strips * P.KS;
         strips += mats[i].w.strips;
     }
@@ -562,13 +673,22 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     P.ws = ws;
     P.counters = counters;
 
+    // Grid: every strip cut into S equal K-ranges (one segment per CTA) or plain stream-K over all resident slots --
+    // whichever has the cheaper slowest CTA under  cost = segments * F + slabs  (F = per-segment fixed cost in slabs).
+    extern int g_tc_ctas_per_sm;
     const int sms = device_sm_count(device);
-    const long long slots = sms;                      // one CTA per SM: leaves TMEM / smem for the next kernel's CTA (PDL)
+    const long long slots = (long long)sms * g_tc_ctas_per_sm;
+    const long long F = 16;
     long long grid_ll = std::min(slots, units);
-    if (strips <= slots) {
-        int S = (int)(slots / strips);
-        while (S > 1 && (P.KS % S) != 0) --S;
-        grid_ll = (long long)strips * S;
+    {
+        const long long L = (units + grid_ll - 1) / grid_ll;
+        const long long cost_stream = ((L + P.KS - 1) / P.KS + 1) * F + L;
+        if (strips <= slots) {
+            int S = (int)(slots / strips);
+            while (S > 1 && (P.KS % S) != 0) --S;
+            const long long cost_aligned = F + P.KS / S;
+            if (cost_aligned <= cost_stream) grid_ll = (long long)strips * S;
+        }
     }
     const int grid = (int)std::max(1ll, grid_ll);
     EXL2B_REQUIRE((units + 1) * grid < (1ll << 31), "problem too large for 32-bit unit arithmetic");
@@ -577,17 +697,48 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     EXL2B_REQUIRE(strips <= n_counters, "too many strips for the counter array");
     EXL2B_REQUIRE((size_t)strips * P.maxc * TC_RED_FLOATS * sizeof(float) <= ws_bytes, "split-K workspace too small");
 
-    const int fixed = TC_SMEM_RINGS + TC_SMEM_B + TC_SMEM_BARS + TC_SMEM_MISC;
+    // stage = the largest group of any matrix of the launch, per 32-column block
+    int stage_bytes = 0;
+    for (int i = 0; i < nm; ++i)
+        for (int r = 0; r < mats[i].w.num_regions; ++r)
+            stage_bytes = std::max(stage_bytes, (1 << mats[i].w.reg[r].spg_log2) * block_bytes(mats[i].w.reg[r].bits));
+    EXL2B_REQUIRE(stage_bytes > 0 && stage_bytes <= 4096, "quantisation groups above 128 rows are not supported by the tcgen05 kernel");
+    const long long seg_max = std::min((long long)P.KS, (units + grid - 1) / grid + 4);      // + group snapping slack
+    P.tc_stage_bytes = stage_bytes;
+    P.tc_act_bytes = (int)(seg_max * SLAB_K * 16);                                           // 16 B per k (8 token slots)
+    const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + 1023) / 1024) * 1024;
+    P.tc_act_off = header;
+    const size_t smem_total = (size_t)header + P.tc_act_bytes + (size_t)TC_WARPS * TC_STAGES * stage_bytes;
+    EXL2B_REQUIRE(smem_total <= 200 * 1024, "K range per CTA too large for shared memory (%zu bytes)", smem_total);
+    EXL2B_REQUIRE((size_t)mats[0].w.K * 16 <= TC_XP_BYTES_PER_MAT, "K too large for the activation scratch");
+    extern unsigned long long* g_dbg;
+    extern int g_dbg_cta, g_dbg_slot;
+    P.dbg_cta = g_dbg_cta;
+
+    PrepParams Q = {};
+    Q.ldx = mats[0].ldx;
+    Q.K = mats[0].w.K;
+    Q.num_mats = nm;
+    Q.norm_w = norm_w;
+    Q.norm_eps = norm_eps;
+    for (int i = 0; i < nm; ++i) {
+        Q.perm[i] = mats[i].w.perm;
+        Q.xp[i] = const_cast<half*>(P.mat[i].xp);
+    }
     for (int m0 = 0; m0 < M; m0 += GEMV_MTOK) {
         P.M = std::min(GEMV_MTOK, M - m0);
+        P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
         for (int i = 0; i < nm; ++i) {
             P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
             P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
         }
+        Q.x = mats[0].x + (size_t)m0 * mats[0].ldx;
+        Q.M = P.M;
+        EXL2B_CUDA(launch_pdl(tc_prep_kernel, dim3(GEMV_MTOK), dim3(1024), 0, stream, Q));
         if (P.M == 1) {
-            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), (size_t)fixed + 1 * 128 * 4, stream, P));
+            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
         } else {
-            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<8>, dim3(grid), dim3(TC_THREADS), (size_t)fixed + 8 * 128 * 4, stream, P));
+            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<8>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
         }
     }
     return 0;

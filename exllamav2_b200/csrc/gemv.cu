@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_cons
 // ---- host launcher -----------------------------------------------------------------------------------------------
 
 int g_ctas_per_sm = 2;
+int g_tc_ctas_per_sm = [] { const char* e = getenv("EXL2B_TC_CTAS"); return e ? atoi(e) : 2; }();
 unsigned long long* g_dbg = nullptr;
 int g_dbg_cta = 0;
 int g_dbg_slot = 0;
@@ -594,7 +595,7 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     P.epilogue = epilogue;
     P.ws = dw->ws;
     P.counters = dw->counters;
-    P.dbg = g_dbg ? g_dbg + 8 * (g_dbg_slot++ % 64) : nullptr;
+    P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
 
     const int sms = device_sm_count(device);
@@ -679,7 +680,7 @@ extern "C" int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_
 
 // ---- tuning / diagnostics hooks (not part of the reference surface) ---------------------------------------------------
 extern "C" int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta) {
-    if (ctas_per_sm > 0) exl2b::g_ctas_per_sm = ctas_per_sm;
+    if (ctas_per_sm > 0) { exl2b::g_ctas_per_sm = ctas_per_sm; exl2b::g_tc_ctas_per_sm = ctas_per_sm; }
     exl2b::g_dbg = stamps;
     exl2b::g_dbg_cta = cta;
     exl2b::g_dbg_slot = 0;

@@ -15,6 +15,7 @@ enum GemvEpilogue : int {
 
 struct GemvMat {
     QMatView w;
+    const half* xp;  // tcgen05 path: activations prepared by tc_prep_kernel (normalised, permuted, UMMA core-matrix layout)
     const half* x;   // input activations fp16 [M][ldx], ORIGINAL feature order (the kernel gathers through w.perm)
     int ldx;
     half* c;         // output fp16 [M][ldc]
@@ -40,6 +41,9 @@ struct GemvParams {
     int act_rows;          // rows staged per segment (capacity)
     unsigned long long* dbg;   // optional phase timestamps (globaltimer) of CTA dbg_cta, NULL in production
     int dbg_cta;
+    int tc_stage_bytes;    // tcgen05 kernel: bytes of one weight stage (largest group of one 32-column block)
+    int tc_act_off;        // tcgen05 kernel: shared-memory offset of the staged activations
+    int tc_act_bytes;      // tcgen05 kernel: capacity of the staged activations (16 B per k)
 };
 
 // Launch one or more passes (8 tokens each) of the GEMV over `nm` matrices that share K and the input layout.

@@ -108,6 +108,16 @@ int main() {
             CHECK(v == (double)(OFFSET4 + (int)vals[p * 2 + e]), "offset form p %d e %d got %f", p, e, v);
         }
     }
+    for (int trial = 0; trial < 64; ++trial) {
+        uint32_t vals[32], mw[8], ew[4], A[16];
+        for (int i = 0; i < 32; ++i) vals[i] = rng() & 15;
+        compose_lane_words(4, vals, mw, ew);
+        dequant_block_4bit_offset2(mw, A);
+        for (int p = 0; p < 16; ++p) for (int e = 0; e < 2; ++e) {
+            double v = h_to_d((uint16_t)(e ? (A[p] >> 16) : A[p]));
+            CHECK(v == (double)(offset2_of_pair(p) + (int)vals[p * 2 + e]), "offset2 form p %d e %d got %f", p, e, v);
+        }
+    }
     (void)b_frag_pos;
     if (fails) { printf("%d checks failed\n", fails); return 1; }
     printf("layout emulation OK\n");

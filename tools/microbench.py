@@ -112,7 +112,7 @@ def main():
 
             if args.phases:
                 nl = min(len(handles), 12)
-                stamps = torch.zeros((64, 8), dtype=torch.int64, device=DEV)
+                stamps = torch.zeros((64, 32), dtype=torch.int64, device=DEV)
                 for cta in (0, 100):
                     stamps.zero_()
                     stamps[:, 6] = 2**62
@@ -127,7 +127,8 @@ def main():
                     for i in range(nl):
                         r = st[i]
                         print(json.dumps({"shape": name, "M": M, "cta": cta, "launch": i, "grid_start": r[6] - t0, "grid_end": r[7] - t0,
-                                          "cta[start,prefetched,wait_done,staged,consumed,done]": [x - t0 for x in r[:6]]}), flush=True)
+                                          "cta[start,prefetched,wait_done,staged,consumed,done]": [x - t0 for x in r[:6]],
+                                          "groups[top,drained,weights,dequant,synced,issued]x3": [(x - t0 if x else 0) for x in r[8:26]]}), flush=True)
             t_eager = time_loop(run_new, 5)
             # graph-captured cycle (no host launch overhead)
             g = torch.cuda.CUDAGraph()
