@@ -232,6 +232,7 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     ms_per_step = ms_total / K
+    assert bool(torch.isfinite(dec.logits).all()), "decode produced non-finite logits"
     value = 1000.0 / ms_per_step
 
     # ---- e2e: host buffers every step --------------------------------------------------------------------------
@@ -258,24 +259,20 @@ def run_ours(args, rank, world):
            "ms_per_step": t_e2e * 1e3}
 
     # ---- roofline of the dominant kernel: exactly the model's GEMV launches, back to back ------------------------
-    x = torch.randn((1, cfg.hidden_size), dtype=torch.half, device=dev)
-    qkv = [torch.empty((1, n), dtype=torch.half, device=dev) for n in (cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim)]
-    ao = torch.randn((1, 1, cfg.num_heads * cfg.head_dim), dtype=torch.half, device=dev)
-    xs = torch.zeros((1, 1, cfg.hidden_size), dtype=torch.half, device=dev)
-    sin, cos = dec.sin, dec.cos
-
-    nt = ext_c.none_tensor
-    norope = [ext_c.make_q_attn(L.input_norm, nt, True, False, cfg.norm_eps, L.q_proj.q_handle, L.k_proj.q_handle, L.v_proj.q_handle,
-                                L.o_proj.q_handle, nt, nt, 64, cfg.hidden_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
-                                cfg.max_seq_len, False, 0, cfg.head_dim, nt, nt, nt, nt, False, True) for L in dec.layers]
-
+    # (the chained decode loop of exllamav2_b200/model.py minus the attention kernel: Q|K|V, O, gate|up, down per layer
+    #  + lm_head -- same handles, same fused epilogues, same buffers as the timed decode step)
     def gemv_only():
-        for L, A in zip(dec.layers, norope):
-            ext_c.q_attn_forward_1(A, xs, 1, 1, 0, nt, qkv[0], qkv[1], qkv[2], sin, cos)    # RMSNorm + Q|K|V GEMV (one launch)
-            ext_c.q_attn_forward_2(A, xs, ao, 1, 1)                                         # O GEMV
-            ext_c.q_mlp_forward_(L.mlp, xs)                                                 # gate|up GEMV (+silu*mul), down GEMV
-        ext_c.gemm_half_q_half(x, dec.lm_head.q_handle, dec.logits, False)
+        if dec.chained and dec.fused_attn:
+            dec._forward_tokens_chained(dec.x, dec.q, dec.k, dec.v, dec.attn_out, 1, head=True, gemv_only=True)
+            ext_c.gemm_half_q_half_prepared(dec.lm_head.q_handle, dec.logits, True, cfg.norm_eps)
+        else:
+            for L in dec.layers:
+                ext_c.q_attn_forward_1(L.attn, dec.x, 1, 1, -1, dec.cache.cache_seqlens, dec.q, dec.k, dec.v, dec.sin, dec.cos)
+                ext_c.q_attn_forward_2(L.attn, dec.x, dec.attn_out, 1, 1)
+                ext_c.q_mlp_forward_(L.mlp, dec.x)
+            ext_c.gemm_half_q_half(dec.xn, dec.lm_head.q_handle, dec.logits, False)
 
+    dec.x.normal_()
     with torch.cuda.stream(s):
         gemv_only()
         torch.cuda.synchronize()
@@ -297,10 +294,10 @@ def run_ours(args, rank, world):
     ms_gemv = e0.elapsed_time(e1) / R
     peak, peak_src = measured_peaks()
     achieved = dec.weight_bytes / (ms_gemv * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_token": dec.weight_bytes,
                 "gemv_launches_per_token": n_gemv, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
-                "note": f"{n_launch_roof} gemv launches replayed back to back in one CUDA graph, CUDA events"}
+                "note": f"{n_launch_roof} launches ({n_gemv} dequant-GEMMs + their prep/rope launches, if any) replayed back to back in one CUDA graph, CUDA events"}
 
     cpu = cpu_port_baseline(cfg) if not args.no_cpu else None
     line = {

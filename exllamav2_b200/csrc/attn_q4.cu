@@ -1,0 +1,339 @@
+// Decode attention straight over the Q4 K/V cache: quantise-and-append the new rows, attend, in ONE kernel.
+//
+// The reference runs, per layer and per step (exllamav2/attn.py:560-613, cache.py:472-556):
+//     q_to_fp16_kv over the WHOLE live cache -> flash_attn_with_kvcache on the fp16 temp -> fp16_to_q_kv of the new rows
+// i.e. it expands every cached nibble to fp16 in HBM and reads it back.  Here the cache is consumed as stored
+// (0.5 B + 1/16 B per value):
+//   * the cache holds y = H32 x per 64-value unit (unnormalised Hadamard on the even / odd interleaved 32-vectors,
+//     cache_q.cuh), quantised to 4 bits with an fp16 scale per 32 consecutive values.  H is symmetric and H H = 32 I, so
+//         q . x = (H q) . y / 32            sum_s p_s x_s = H (sum_s p_s y_s) / 32
+//     the query is rotated ONCE, scores and the P V sum are formed on the stored (rotated) values, and the output is
+//     rotated back ONCE -- no per-position butterflies.
+//   * the q_len new K/V rows are quantised with exactly the arithmetic of fp16_to_q_kv (kvcache.cu pack_unit_q4, same
+//     bits as the reference) and written to the paged cache by one designated CTA per kv head.  The step that appends
+//     them attends them UNQUANTISED (fp16 values, rotated in fp32), exactly like the reference, where
+//     flash_attn_with_kvcache sees the fp16 rows and the cache only quantises them afterwards (attn.py:602-621).
+// One CTA per (head, sequence); decode regime (q_len <= 8).
+#include "qmatrix.cuh"
+
+namespace exl2b {
+
+constexpr int AQ_THREADS = 256;
+constexpr int AQ_WARPS = 8;
+constexpr int AQ_MAX_QLEN = 8;
+
+struct AttnQ4Params {
+    const half* q;          // [batch, q_len, H, hd]     (RoPE already applied)
+    const half* k_new;      // [batch, q_len, KVH, hd]
+    const half* v_new;
+    uint8_t* k_q;           // [pages, page_size, KVH, hd/2]
+    half* k_s;              // [pages, page_size, KVH, hd/32]
+    uint8_t* v_q;
+    half* v_s;
+    const int32_t* cache_seqlens;   // [batch]  tokens already in the cache
+    const int32_t* block_table;     // [batch, pages_per_seq]
+    half* out;              // [batch, q_len, H, hd]
+    half* out_xp;           // optional: the consumer matrix's (o_proj) activation buffer, UMMA layout, permuted rows
+    const uint16_t* out_invperm;
+    int q_len, H, KVH, hd, page_size, pages_per_seq, max_ctx;
+    float scale_log2;       // softmax_scale * log2(e)
+};
+
+// fp32 Hadamard-32 across the warp on both halves of a float2 (same butterfly as cache_q.cuh, exact sign handling)
+__device__ __forceinline__ float2 hadamard32_f(float2 w, int lane) {
+#pragma unroll
+    for (int i = 1; i < 32; i <<= 1) {
+        const float px = __shfl_xor_sync(0xffffffffu, w.x, i), py = __shfl_xor_sync(0xffffffffu, w.y, i);
+        const float sg = (lane & i) ? -1.f : 1.f;
+        w.x = fmaf(sg, w.x, px);
+        w.y = fmaf(sg, w.y, py);
+    }
+    return w;
+}
+
+__device__ __forceinline__ half2 hadamard32_h(half2 w2, int lane) {      // bit-identical to kvcache.cu hadamard32
+#pragma unroll
+    for (int i = 1; i < 32; i <<= 1) {
+        const half2 pw2 = __shfl_xor_sync(0xffffffffu, w2, i);
+        uint32_t* w2i = reinterpret_cast<uint32_t*>(&w2);
+        const int32_t sfm = -static_cast<int32_t>(lane & i) >> 31;
+        *w2i ^= (sfm & 0x80008000);
+        w2 = __hadd2(w2, pw2);
+    }
+    return w2;
+}
+
+// (nibble - 8) as fp32 without I2F: 0x4B000000 | n is the float 2^23 + n
+__device__ __forceinline__ float nib_f(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388616.0f; }
+
+template <int HD>
+__global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_constant__ AttnQ4Params P) {
+    constexpr int ROWB = HD / 2;            // packed bytes per (position, kv head)
+    constexpr int NSC = HD / 32;            // scales per (position, kv head)
+    constexpr int VEC = HD / 32;            // values per lane in the dims-on-lanes phase
+    constexpr int UNITS = HD / 64;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = P.H / P.KVH, kvh = h / group;
+
+    float* qrot = reinterpret_cast<float*>(smem);                          // [HD]
+    float* red = qrot + HD;                                                // [AQ_WARPS][HD]
+    float* wred = red + AQ_WARPS * HD;                                     // [2 * AQ_WARPS]
+    uint8_t* new_q = reinterpret_cast<uint8_t*>(wred + 2 * AQ_WARPS);      // [2][AQ_MAX_QLEN][ROWB]
+    half* new_s = reinterpret_cast<half*>(new_q + 2 * AQ_MAX_QLEN * ROWB); // [2][AQ_MAX_QLEN][NSC]
+    float* new_y = reinterpret_cast<float*>(new_s + 2 * AQ_MAX_QLEN * NSC);// [2][AQ_MAX_QLEN][HD] rotated, unquantised new rows
+    int* pages_s = reinterpret_cast<int*>(new_y + 2 * AQ_MAX_QLEN * HD);   // [pages_per_seq]
+    float* sc = reinterpret_cast<float*>(pages_s + ((P.pages_per_seq + 3) & ~3));   // [max_ctx + q_len]
+
+    griddep_launch_dependents();
+    griddep_wait();
+    const int seqlen = P.cache_seqlens[b];
+    for (int i = tid; i < P.pages_per_seq; i += AQ_THREADS) pages_s[i] = P.block_table[(size_t)b * P.pages_per_seq + i];
+    const int* bt = pages_s;
+
+    // ---- 1. quantise the new rows (fp16_to_q_kv arithmetic), keep them in shared memory, one CTA per kv head stores them
+    for (int job = warp; job < 2 * P.q_len * UNITS; job += AQ_WARPS) {
+        const int kv = job / (P.q_len * UNITS), r = job - kv * P.q_len * UNITS;
+        const int i = r / UNITS, un = r - i * UNITS;
+        const half* src = (kv ? P.v_new : P.k_new) + (((size_t)b * P.q_len + i) * P.KVH + kvh) * HD + un * 64;
+        half2 w2 = reinterpret_cast<const half2*>(src)[lane];
+        {
+            const float2 y = hadamard32_f(__half22float2(w2), lane);
+            new_y[(kv * AQ_MAX_QLEN + i) * HD + un * 64 + 2 * lane] = y.x;
+            new_y[(kv * AQ_MAX_QLEN + i) * HD + un * 64 + 2 * lane + 1] = y.y;
+        }
+        w2 = hadamard32_h(w2, lane);
+        half2 absmax2 = __habs2(w2);
+        half absmax = __hmax(__low2half(absmax2), __high2half(absmax2));
+        absmax = __hmax(absmax, __shfl_xor_sync(0xffffffffu, absmax, 8));
+        absmax = __hmax(absmax, __shfl_xor_sync(0xffffffffu, absmax, 4));
+        absmax = __hmax(absmax, __shfl_xor_sync(0xffffffffu, absmax, 2));
+        absmax = __hmax(absmax, __shfl_xor_sync(0xffffffffu, absmax, 1));
+        const half2 c_8 = __half2half2(__float2half_rn(8));
+        w2 = __h2div(w2, __half2half2(absmax));
+        w2 = __hfma2(w2, c_8, c_8);
+        const int q0 = min(max(__half2int_rn(__low2half(w2)), 0), 15);
+        const int q1 = min(max(__half2int_rn(__high2half(w2)), 0), 15);
+        new_q[(kv * AQ_MAX_QLEN + i) * ROWB + un * 32 + lane] = (uint8_t)(q0 | (q1 << 4));
+        if ((lane & 15) == 0) new_s[(kv * AQ_MAX_QLEN + i) * NSC + un * 2 + (lane >> 4)] = __hmul(absmax, __float2half_rn(1.0f / 8.0f));
+    }
+    __syncthreads();
+    if (h % group == 0) {
+        for (int idx = tid; idx < 2 * P.q_len * (ROWB / 4); idx += AQ_THREADS) {
+            const int kv = idx / (P.q_len * (ROWB / 4)), r = idx - kv * P.q_len * (ROWB / 4);
+            const int i = r / (ROWB / 4), wd = r - i * (ROWB / 4);
+            const int pos = seqlen + i;
+            const int page = bt[pos / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
+            reinterpret_cast<uint32_t*>((kv ? P.v_q : P.k_q) + row * ROWB)[wd] =
+                reinterpret_cast<const uint32_t*>(new_q + (kv * AQ_MAX_QLEN + i) * ROWB)[wd];
+        }
+        for (int idx = tid; idx < 2 * P.q_len * NSC; idx += AQ_THREADS) {
+            const int kv = idx / (P.q_len * NSC), r = idx - kv * P.q_len * NSC;
+            const int i = r / NSC, s = r - i * NSC;
+            const int pos = seqlen + i;
+            const int page = bt[pos / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
+            (kv ? P.v_s : P.k_s)[row * NSC + s] = new_s[(kv * AQ_MAX_QLEN + i) * NSC + s];
+        }
+    }
+
+    for (int i = 0; i < P.q_len; ++i) {
+        const int n_ctx = seqlen + i + 1;
+        // ---- 2. rotate the query once: qrot = H q * (softmax_scale * log2 e / 32) ----
+        if (warp < UNITS) {
+            const half2 qh = reinterpret_cast<const half2*>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD + warp * 64)[lane];
+            float2 w = hadamard32_f(__half22float2(qh), lane);
+            const float f = P.scale_log2 * (1.0f / 32.0f);
+            qrot[warp * 64 + 2 * lane] = w.x * f;
+            qrot[warp * 64 + 2 * lane + 1] = w.y * f;
+        }
+        __syncthreads();
+
+        // ---- 3. scores: one position per thread, the whole (rotated) row against qrot ----
+        float lmax = -INFINITY;
+        for (int p = tid; p < n_ctx; p += AQ_THREADS) {
+            if (p >= seqlen) {                   // a row appended by this step: fp16 values, rotated in fp32
+                const float* y = new_y + (p - seqlen) * HD;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < HD; j += 4) {
+                    s0 = fmaf(qrot[j], y[j], s0);
+                    s1 = fmaf(qrot[j + 1], y[j + 1], s1);
+                    s2 = fmaf(qrot[j + 2], y[j + 2], s2);
+                    s3 = fmaf(qrot[j + 3], y[j + 3], s3);
+                }
+                const float s = (s0 + s1) + (s2 + s3);
+                sc[p] = s;
+                lmax = fmaxf(lmax, s);
+                continue;
+            }
+            const int page = bt[p / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
+            const uint8_t* kq = P.k_q + row * ROWB;
+            const half* ks = P.k_s + row * NSC;
+            float s = 0.f;
+#pragma unroll
+            for (int blk = 0; blk < NSC; ++blk) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(kq + blk * 16);
+                const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 qa = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8);
+                    const float4 qb = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8 + 4);
+                    const uint32_t x = ww[j];
+                    a = fmaf(nib_f(x & 15u), qa.x, a);
+                    a = fmaf(nib_f((x >> 4) & 15u), qa.y, a);
+                    a = fmaf(nib_f((x >> 8) & 15u), qa.z, a);
+                    a = fmaf(nib_f((x >> 12) & 15u), qa.w, a);
+                    a = fmaf(nib_f((x >> 16) & 15u), qb.x, a);
+                    a = fmaf(nib_f((x >> 20) & 15u), qb.y, a);
+                    a = fmaf(nib_f((x >> 24) & 15u), qb.z, a);
+                    a = fmaf(nib_f(x >> 28), qb.w, a);
+                }
+                s = fmaf(__half2float(ks[blk]), a, s);
+            }
+            sc[p] = s;
+            lmax = fmaxf(lmax, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) wred[warp] = lmax;
+        __syncthreads();
+        float mx = wred[0];
+#pragma unroll
+        for (int w = 1; w < AQ_WARPS; ++w) mx = fmaxf(mx, wred[w]);
+        float lsum = 0.f;
+        for (int p = tid; p < n_ctx; p += AQ_THREADS) {
+            const float e = exp2f(sc[p] - mx);
+            sc[p] = e;
+            lsum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if (lane == 0) wred[AQ_WARPS + warp] = lsum;
+        __syncthreads();
+        float denom = 0.f;
+#pragma unroll
+        for (int w = 0; w < AQ_WARPS; ++w) denom += wred[AQ_WARPS + w];
+
+        // ---- 4. P V in the rotated domain: lane = VEC consecutive values, warps stride over positions ----
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        constexpr int PV_UNROLL = 8;
+        for (int p0 = warp; p0 < seqlen; p0 += AQ_WARPS * PV_UNROLL) {       // cached rows: all loads of 8 positions in flight
+            uint32_t xq[PV_UNROLL];
+            float pe[PV_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PV_UNROLL; ++u) {
+                const int p = p0 + u * AQ_WARPS;
+                xq[u] = 0x8888u;
+                pe[u] = 0.f;
+                if (p < seqlen) {
+                    const int page = bt[p / P.page_size];
+                    const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
+                    if constexpr (VEC == 4) xq[u] = *reinterpret_cast<const uint16_t*>(P.v_q + row * ROWB + lane * 2);
+                    else xq[u] = P.v_q[row * ROWB + lane];
+                    pe[u] = sc[p] * __half2float(P.v_s[row * NSC + ((lane * VEC) >> 5)]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PV_UNROLL; ++u) {
+                const uint32_t x = xq[u];
+                if constexpr (VEC == 4) {
+                    acc[0] = fmaf(pe[u], nib_f(x & 15u), acc[0]);
+                    acc[1] = fmaf(pe[u], nib_f((x >> 4) & 15u), acc[1]);
+                    acc[2] = fmaf(pe[u], nib_f((x >> 8) & 15u), acc[2]);
+                    acc[3] = fmaf(pe[u], nib_f((x >> 12) & 15u), acc[3]);
+                } else {
+                    acc[0] = fmaf(pe[u], nib_f(x & 15u), acc[0]);
+                    acc[1] = fmaf(pe[u], nib_f((x >> 4) & 15u), acc[1]);
+                }
+            }
+        }
+        if (warp == 0) {                                                      // rows appended by this step (<= 8)
+            for (int p = seqlen; p < n_ctx; ++p) {
+                const float pe = sc[p];
+                const float* y = new_y + (AQ_MAX_QLEN + p - seqlen) * HD + lane * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(pe, y[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) red[warp * HD + lane * VEC + j] = acc[j];
+        __syncthreads();
+        // ---- 5. sum over warps, rotate back (x = H y / 32), normalise, store ----
+        if (warp < UNITS) {
+            float2 w = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int ww = 0; ww < AQ_WARPS; ++ww) {
+                w.x += red[ww * HD + warp * 64 + 2 * lane];
+                w.y += red[ww * HD + warp * 64 + 2 * lane + 1];
+            }
+            w = hadamard32_f(w, lane);
+            const float f = (1.0f / 32.0f) / denom;
+            const half2 o2 = __floats2half2_rn(w.x * f, w.y * f);
+            reinterpret_cast<half2*>(P.out + (((size_t)b * P.q_len + i) * P.H + h) * HD + warp * 64)[lane] = o2;
+            if (P.out_xp) {
+                const int n = h * HD + warp * 64 + 2 * lane, m = b * P.q_len + i;
+                const int k0 = P.out_invperm ? (int)P.out_invperm[n] : n, k1 = P.out_invperm ? (int)P.out_invperm[n + 1] : n + 1;
+                P.out_xp[(size_t)(k0 >> 3) * 64 + m * 8 + (k0 & 7)] = __low2half(o2);
+                P.out_xp[(size_t)(k1 >> 3) * 64 + m * 8 + (k1 & 7)] = __high2half(o2);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace exl2b
+
+using namespace exl2b;
+
+extern "C" int exl2b_paged_attn_decode_q4(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint8_t* k_cache,
+                                          uint16_t* k_scales, uint8_t* v_cache, uint16_t* v_scales, const int32_t* cache_seqlens,
+                                          const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
+                                          int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
+                                          exl2b_qmatrix_t out_consumer, exl2b_stream_t stream) {
+    EXL2B_REQUIRE(q && k_new && v_new && k_cache && k_scales && v_cache && v_scales && cache_seqlens && block_table && out, "null argument");
+    EXL2B_REQUIRE(head_dim == 64 || head_dim == 128, "head_dim %d not supported (64 or 128)", head_dim);
+    EXL2B_REQUIRE(num_heads % num_kv_heads == 0, "bad GQA ratio");
+    EXL2B_REQUIRE(q_len >= 1 && q_len <= AQ_MAX_QLEN, "q_len %d outside the decode regime (1..%d)", q_len, AQ_MAX_QLEN);
+    AttnQ4Params P = {};
+    P.q = (const half*)q; P.k_new = (const half*)k_new; P.v_new = (const half*)v_new;
+    P.k_q = k_cache; P.k_s = (half*)k_scales; P.v_q = v_cache; P.v_s = (half*)v_scales;
+    P.cache_seqlens = cache_seqlens; P.block_table = block_table; P.out = (half*)out;
+    P.q_len = q_len; P.H = num_heads; P.KVH = num_kv_heads; P.hd = head_dim;
+    P.page_size = page_size; P.pages_per_seq = pages_per_seq;
+    P.max_ctx = page_size * pages_per_seq;
+    P.scale_log2 = softmax_scale * 1.4426950408889634f;
+    if (out_consumer) {
+        QMatrix* oc = (QMatrix*)out_consumer;
+        EXL2B_REQUIRE(oc->v.layout == LAYOUT_TC && oc->v.K == num_heads * head_dim, "out_consumer does not take the attention output");
+        EXL2B_REQUIRE(batch * q_len <= 8, "chained attention output needs at most 8 rows");
+        int rc = qmatrix_chain_buffers(oc);
+        if (rc) return rc;
+        P.out_xp = oc->xp_buf;
+        P.out_invperm = oc->invperm;
+    }
+    const int hd = head_dim;
+    const size_t smem = (size_t)(hd + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
+                        (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)(P.max_ctx + q_len) * 4;
+    EXL2B_REQUIRE(smem <= 200 * 1024, "context of %d tokens does not fit the score buffer", P.max_ctx);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EXL2B_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev]) {
+        EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[dev] = true;
+    }
+    dim3 grid(num_heads, batch);
+    if (head_dim == 128)
+        EXL2B_CUDA(launch_pdl(attn_q4_kernel<128>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
+    else
+        EXL2B_CUDA(launch_pdl(attn_q4_kernel<64>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
+    return 0;
+}

@@ -34,6 +34,35 @@ static GemvMat make_mat(const QMatrix* q, const half* x, int ldx, half* c, int l
     return m;
 }
 
+// epilogue of a producer launch -> the consumers' activation buffers (+ sums of squares when they apply an RMSNorm)
+static int chain_out(GemvExtras& ex, const exl2b_chain_t* next) {
+    if (!next || next->num_consumers <= 0) return 0;
+    EXL2B_REQUIRE(next->num_consumers <= GEMV_MAX_MATS, "at most %d chained consumers", GEMV_MAX_MATS);
+    for (int i = 0; i < next->num_consumers; ++i) {
+        QMatrix* c = (QMatrix*)next->consumers[i];
+        EXL2B_REQUIRE(c && c->v.layout == LAYOUT_TC, "chained consumer must be a tcgen05-layout matrix");
+        int rc = qmatrix_chain_buffers(c);
+        if (rc) return rc;
+        ex.scat[i] = ScatterTarget{c->xp_buf, c->invperm, (const half*)next->norm_weight};
+    }
+    ex.num_scat = next->num_consumers;
+    if (next->norm_weight) ex.sumsq_out = ((QMatrix*)next->consumers[0])->sumsq_buf;
+    return 0;
+}
+// consumer side: the matrices' inputs were written by a chained producer
+static int chain_in(GemvExtras& ex, GemvMat* mats, const QMatrix* const* qs, int nm, bool has_norm) {
+    ex.prepared = 1;
+    for (int i = 0; i < nm; ++i) {
+        EXL2B_REQUIRE(qs[i]->xp_buf, "input_prepared set, but no chained producer has written this matrix's input");
+        mats[i].xp = qs[i]->xp_buf;
+    }
+    if (has_norm) {
+        ex.sumsq_in = qs[0]->sumsq_buf;
+        ex.sumsq_in_strips = (qs[0]->v.K + 127) / 128;
+    }
+    return 0;
+}
+
 }  // namespace exl2b
 
 using namespace exl2b;
@@ -58,11 +87,11 @@ extern "C" int exl2b_qattn_destroy(exl2b_qattn_t h) {
     return 0;
 }
 
-extern "C" int exl2b_qattn_forward_1(exl2b_qattn_t h, const uint16_t* x, int batch, int q_len, int past_len,
-                                     const int32_t* past_lens, uint16_t* q, uint16_t* k, uint16_t* v, const uint16_t* sin,
-                                     const uint16_t* cos, exl2b_stream_t stream_) {
+extern "C" int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int batch, int q_len, int past_len,
+                                        const int32_t* past_lens, uint16_t* q, uint16_t* k, uint16_t* v, const uint16_t* sin,
+                                        const uint16_t* cos, int input_prepared, exl2b_stream_t stream_) {
     QAttn* a = (QAttn*)h;
-    EXL2B_REQUIRE(a && x && q && k && v, "null argument");
+    EXL2B_REQUIRE(a && q && k && v && (x || input_prepared), "null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     EXL2B_CUDA(cudaSetDevice(a->device));
     const exl2b_qattn_desc& d = a->d;
@@ -73,10 +102,23 @@ extern "C" int exl2b_qattn_forward_1(exl2b_qattn_t h, const uint16_t* x, int bat
         make_mat(mk, (const half*)x, d.hidden_size, (half*)k, mk->v.N, 1),
         make_mat(mv, (const half*)x, d.hidden_size, (half*)v, mv->v.N, 1),
     };
+    const bool rope = d.rope_style != 0;
+    if (rope) EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
+    const bool fuse = gemv_supports_extras(mats, 3, rows) && (!rope || (d.head_dim <= 128 && 128 % d.head_dim == 0 && d.sincos_size <= d.head_dim));
+    EXL2B_REQUIRE(!input_prepared || fuse, "input_prepared needs the tcgen05 layout and at most %d rows", GEMV_MTOK);
+    if (fuse) {
+        GemvExtras ex = {};
+        if (rope) ex.rope = RopeFuse{(const half*)sin, (const half*)cos, past_lens, past_len, q_len, d.head_dim, d.sincos_size, d.rope_style == 2, 3u};
+        if (input_prepared) {
+            const QMatrix* qs[3] = {mq, mk, mv};
+            int rc = chain_in(ex, mats, qs, 3, d.layernorm != nullptr);
+            if (rc) return rc;
+        }
+        return gemv_launch(a->device, stream, mats, 3, rows, (const half*)d.layernorm, d.norm_epsilon, EPI_STORE, &ex);
+    }
     int rc = gemv_launch(a->device, stream, mats, 3, rows, (const half*)d.layernorm, d.norm_epsilon, EPI_STORE);
     if (rc) return rc;
-    if (d.rope_style != 0) {
-        EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
+    if (rope) {
         const int neox = d.rope_style == 2;
         rc = rope_launch(stream, (half*)q, (const half*)sin, (const half*)cos, batch, q_len * d.num_heads, d.head_dim, d.num_heads,
                          past_len, past_lens, neox, d.sincos_size);
@@ -87,14 +129,37 @@ extern "C" int exl2b_qattn_forward_1(exl2b_qattn_t h, const uint16_t* x, int bat
     return rc;
 }
 
-extern "C" int exl2b_qattn_forward_2(exl2b_qattn_t h, uint16_t* x, const uint16_t* attn_out, int batch, int q_len,
-                                     exl2b_stream_t stream) {
+extern "C" int exl2b_qattn_forward_1(exl2b_qattn_t h, const uint16_t* x, int batch, int q_len, int past_len,
+                                     const int32_t* past_lens, uint16_t* q, uint16_t* k, uint16_t* v, const uint16_t* sin,
+                                     const uint16_t* cos, exl2b_stream_t stream) {
+    EXL2B_REQUIRE(x, "null argument");
+    return exl2b_qattn_forward_1_ex(h, x, batch, q_len, past_len, past_lens, q, k, v, sin, cos, 0, stream);
+}
+
+extern "C" int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint16_t* attn_out, int batch, int q_len,
+                                        int input_prepared, const exl2b_chain_t* next, exl2b_stream_t stream) {
     QAttn* a = (QAttn*)h;
-    EXL2B_REQUIRE(a && x && attn_out, "null argument");
+    EXL2B_REQUIRE(a && x && (attn_out || input_prepared), "null argument");
     EXL2B_CUDA(cudaSetDevice(a->device));
     const QMatrix* mo = (const QMatrix*)a->d.o_proj;
     GemvMat m = make_mat(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, a->d.has_residual ? 0 : 1);
-    return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
+    const bool want = input_prepared || (next && next->num_consumers > 0);
+    if (!want) return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
+    EXL2B_REQUIRE(gemv_supports_extras(&m, 1, batch * q_len), "chained launches need the tcgen05 layout and at most %d rows", GEMV_MTOK);
+    GemvExtras ex = {};
+    int rc = chain_out(ex, next);
+    if (rc) return rc;
+    if (input_prepared) {
+        rc = chain_in(ex, &m, &mo, 1, false);
+        if (rc) return rc;
+    }
+    return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE, &ex);
+}
+
+extern "C" int exl2b_qattn_forward_2(exl2b_qattn_t h, uint16_t* x, const uint16_t* attn_out, int batch, int q_len,
+                                     exl2b_stream_t stream) {
+    EXL2B_REQUIRE(attn_out, "null argument");
+    return exl2b_qattn_forward_2_ex(h, x, attn_out, batch, q_len, 0, nullptr, stream);
 }
 
 extern "C" int exl2b_qmlp_create(const exl2b_qmlp_desc* d, exl2b_qmlp_t* out) {
@@ -115,8 +180,8 @@ extern "C" int exl2b_qmlp_destroy(exl2b_qmlp_t h) {
     return 0;
 }
 
-extern "C" int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b,
-                                  exl2b_stream_t stream_) {
+extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b,
+                                     int input_prepared, const exl2b_chain_t* next, exl2b_stream_t stream_) {
     (void)temp_b;    // the up projection never materialises: silu(gate)*up is formed in the GEMV epilogue
     QMlp* m = (QMlp*)h;
     EXL2B_REQUIRE(m && x && temp_a, "null argument");
@@ -128,9 +193,68 @@ extern "C" int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_
         make_mat(g, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
         make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
     };
-    int rc = gemv_launch(m->device, stream, gu, 2, rows, (const half*)d.layernorm, d.norm_epsilon,
-                         d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL);
-    if (rc) return rc;
     GemvMat down = make_mat(dn, (const half*)temp_a, d.intermediate_size, (half*)x, d.hidden_size, d.has_residual ? 0 : 1);
-    return gemv_launch(m->device, stream, &down, 1, rows, nullptr, 0.f, EPI_STORE);
+    const int epi = d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL;
+    const bool fuse = gemv_supports_extras(gu, 2, rows) && gemv_supports_extras(&down, 1, rows);
+    EXL2B_REQUIRE(fuse || (!input_prepared && !(next && next->num_consumers > 0)),
+                  "chained launches need the tcgen05 layout and at most %d rows", GEMV_MTOK);
+    if (!fuse) {
+        int rc = gemv_launch(m->device, stream, gu, 2, rows, (const half*)d.layernorm, d.norm_epsilon, epi);
+        if (rc) return rc;
+        return gemv_launch(m->device, stream, &down, 1, rows, nullptr, 0.f, EPI_STORE);
+    }
+    // gate|up writes silu(gate)*up straight into down's activation buffer (permuted, UMMA layout): no prep launch between
+    GemvExtras e1 = {};
+    exl2b_chain_t to_down = {};
+    to_down.consumers[0] = (exl2b_qmatrix_t)dn;
+    to_down.num_consumers = 1;
+    int rc = chain_out(e1, &to_down);
+    if (rc) return rc;
+    if (input_prepared) {
+        const QMatrix* qs[2] = {g, u};
+        rc = chain_in(e1, gu, qs, 2, d.layernorm != nullptr);
+        if (rc) return rc;
+    }
+    rc = gemv_launch(m->device, stream, gu, 2, rows, (const half*)d.layernorm, d.norm_epsilon, epi, &e1);
+    if (rc) return rc;
+    GemvExtras e2 = {};
+    rc = chain_out(e2, next);
+    if (rc) return rc;
+    rc = chain_in(e2, &down, &dn, 1, false);
+    if (rc) return rc;
+    return gemv_launch(m->device, stream, &down, 1, rows, nullptr, 0.f, EPI_STORE, &e2);
+}
+
+extern "C" int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b,
+                                  exl2b_stream_t stream) {
+    return exl2b_qmlp_forward_ex(h, x, rows, temp_a, temp_b, 0, nullptr, stream);
+}
+
+// gemm_half_q_half whose input was prepared by a chained producer (lm_head after the last MLP: the final RMSNorm is the
+// producer's scatter scale + this launch's deferred 1/rms)
+extern "C" int exl2b_gemm_half_q_half_prepared(exl2b_qmatrix_t h, uint16_t* c, int ldc, int m, int clear, int has_norm,
+                                               float norm_eps, exl2b_stream_t stream) {
+    QMatrix* q = (QMatrix*)h;
+    EXL2B_REQUIRE(q && c, "null argument");
+    EXL2B_REQUIRE(ldc >= q->v.N, "leading dimension too small");
+    EXL2B_CUDA(cudaSetDevice(q->device));
+    GemvMat mt = make_mat(q, nullptr, q->v.K, (half*)c, ldc, clear ? 1 : 0);
+    EXL2B_REQUIRE(gemv_supports_extras(&mt, 1, m), "chained launches need the tcgen05 layout and at most %d rows", GEMV_MTOK);
+    GemvExtras ex = {};
+    const QMatrix* qc = q;
+    int rc = chain_in(ex, &mt, &qc, 1, has_norm != 0);
+    if (rc) return rc;
+    return gemv_launch(q->device, (cudaStream_t)stream, &mt, 1, m, nullptr, norm_eps, EPI_STORE, &ex);
+}
+
+// the activation buffer a chained producer outside this file (the attention kernel) writes for matrix h
+extern "C" int exl2b_qmatrix_chain_target(exl2b_qmatrix_t h, uint16_t** xp, const uint16_t** invperm) {
+    QMatrix* q = (QMatrix*)h;
+    EXL2B_REQUIRE(q && xp && invperm, "null argument");
+    EXL2B_REQUIRE(q->v.layout == LAYOUT_TC, "chained consumer must be a tcgen05-layout matrix");
+    int rc = qmatrix_chain_buffers(q);
+    if (rc) return rc;
+    *xp = (uint16_t*)q->xp_buf;
+    *invperm = q->invperm;
+    return 0;
 }

@@ -283,7 +283,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     uint8_t* misc = smem + TC_SMEM_BARS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
     int* flag_s = reinterpret_cast<int*>(misc + 64);
-    float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [MT][128]
+    float* rstd_s = reinterpret_cast<float*>(misc + 16);             // [8] deferred RMSNorm factors
+    float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [8][128] WG1 totals
+    half* tile_s = reinterpret_cast<half*>(comb_s + GEMV_MTOK * 128);   // [8][128] fp16 outputs (RoPE partner exchange)
+    float* ssq_s = reinterpret_cast<float*>(tile_s + GEMV_MTOK * 128);  // [4][8] per-warp sums of squares
     const uint32_t act_a = smem0 + P.tc_act_off;
     const int ring_off = P.tc_act_off + P.tc_act_bytes;
     uint8_t* ring_p = smem + ring_off + warp * TC_STAGES * stage_bytes;
@@ -327,6 +330,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
     uint32_t phases = 0, mma_phase = 0, act_phase = 0;
     bool waited = false;
+    auto after_wait = [&]() {       // first point where the previous kernel's output may be read
+        if (P.ex.sumsq_in) {        // warp m: 1/rms of token m, strips summed in a fixed order
+            float sum = 0.f;
+            for (int sidx = lane; sidx < P.ex.sumsq_in_strips; sidx += 32) sum += __ldcg(P.ex.sumsq_in + sidx * 8 + warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) rstd_s[warp] = rsqrtf(sum / (float)(KS * SLAB_K) + P.ex.sumsq_eps);
+        }
+    };
     int u = u0;
     while (u < u1) {
         int mi = 0;
@@ -465,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             if (!waited) {
                 griddep_wait();
                 waited = true;
+                after_wait();
                 TC_STAMP(2);
             }
             if (!act_issued) {           // the segment's activations (UMMA layout, written by tc_prep_kernel): one bulk copy
@@ -523,6 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         if (!waited) {                   // a CTA whose snapped range is empty still takes part in the fix-up below
             griddep_wait();
             waited = true;
+            after_wait();
         }
         TC_STAMP(4);
 
@@ -539,23 +553,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int first_cta = tc_cta_of_unit(sb, G, U), last_cta = tc_cta_of_unit(sb + KS - 1, G, U);
         const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
         const bool paired = P.epilogue != EPI_STORE;
-        auto epilogue_store = [&](int m, float v) {
-            if (n_col < w.N && m < M) {
-                if (w.bias) v += __half2float(w.bias[n_col]);
-                half* cp = mt.c + (size_t)m * mt.ldc + n_col;
-                if (!mt.clear) v += __half2float(*cp);
-                *cp = __float2half_rn(v);
-            }
-        };
+        const bool has_rstd = P.ex.sumsq_in != nullptr;
         if (wg == 0) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) tot[m] += comb_s[m * 128 + tidw];
         }
-        if (nc == 1 && !paired) {
-            if (wg == 0) {
+        // fin / fin2: the strip's complete fp32 sums (fin2 = the up projection of a gate/up pair), held by the finishing CTA
+        bool finisher = false;
+        float fin[MT], fin2[MT];
 #pragma unroll
-                for (int m = 0; m < MT; ++m) epilogue_store(m, tot[m]);
-            }
+        for (int m = 0; m < MT; ++m) { fin[m] = tot[m]; fin2[m] = 0.f; }
+        if (nc == 1 && !paired) {
+            finisher = true;
         } else {
             float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * TC_RED_FLOATS;
             if (wg == 0) {
@@ -577,6 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             }
             __syncthreads();
             if (*flag_s) {
+                finisher = true;
                 __threadfence();
                 if (wg == 0) {
                     if (!paired) {
@@ -585,7 +595,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                         for (int m = 0; m < MT; ++m) {
                             float v = 0.f;
                             for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
-                            epilogue_store(m, v);
+                            fin[m] = v;
                         }
                     } else {
                         const GemvMat& mg = P.mat[0];
@@ -601,17 +611,97 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                             float vg = 0.f, vu = 0.f;
                             for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
                             for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
-                            if (n_col < mg.w.N && m < M) {
-                                if (mg.w.bias) vg += __half2float(mg.w.bias[n_col]);
-                                if (mu.w.bias) vu += __half2float(mu.w.bias[n_col]);
-                                const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);   // q_mlp.cu:187-196 roundings
-                                const half act = (P.epilogue == EPI_GELU_MUL) ? tc_gelu_h(hg) : tc_silu_h(hg);
-                                mg.c[(size_t)m * mg.ldc + n_col] = __hmul(act, hu);
-                            }
+                            fin[m] = vg;
+                            fin2[m] = vu;
                         }
                     }
                 }
                 if (tid == 0) P.counters[cidx] = 0u;
+            }
+        }
+
+        // ---- the finishing CTA's first warpgroup turns the sums into outputs (thread = column) ----
+        if (finisher && wg == 0) {
+            const GemvMat& mo = paired ? P.mat[0] : mt;         // where the result goes
+            const bool col_ok = n_col < mo.w.N;
+            half hv[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const float rs = has_rstd ? rstd_s[m] : 1.f;
+                if (paired) {
+                    float vg = fin[m] * rs, vu = fin2[m] * rs;
+                    if (col_ok && P.mat[0].w.bias) vg += __half2float(P.mat[0].w.bias[n_col]);
+                    if (col_ok && P.mat[1].w.bias) vu += __half2float(P.mat[1].w.bias[n_col]);
+                    const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);           // q_mlp.cu:187-196 roundings
+                    const half act = (P.epilogue == EPI_GELU_MUL) ? tc_gelu_h(hg) : tc_silu_h(hg);
+                    hv[m] = __hmul(act, hu);
+                } else {
+                    float v = fin[m] * rs;
+                    if (col_ok && m < M) {
+                        if (w.bias) v += __half2float(w.bias[n_col]);
+                        if (!mt.clear) v += __half2float(mt.c[(size_t)m * mt.ldc + n_col]);
+                    }
+                    hv[m] = __float2half_rn(v);
+                }
+            }
+            if ((P.ex.rope.mask >> mi) & 1u) {          // RoPE on the fp16 values, partner through shared memory
+                const RopeFuse& R = P.ex.rope;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tile_s[m * 128 + tidw] = hv[m];
+                bar_sync(3, 128);
+                const int d = tidw % R.head_dim, S = R.sincos_size, hd2 = S >> 1;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    if (m < M && d < S) {
+                        const int row = P.row0 + m, bb = row / R.q_len, tt = row - bb * R.q_len;
+                        int base = R.past_len;
+                        if (base == -1) base = max(R.past_lens[bb], 0);
+                        else if (R.past_lens) base += R.past_lens[bb];
+                        const size_t sr = (size_t)max(base + tt, 0) * S;
+                        if (R.neox) {
+                            if (d < hd2) {
+                                const half c = R.cos[sr + d], sn = R.sin[sr + d];
+                                hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw + hd2], __hneg(sn)));
+                            } else {
+                                const half c = R.cos[sr + d - hd2], sn = R.sin[sr + d - hd2];
+                                hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw - hd2], sn));
+                            }
+                        } else {
+                            const half c = R.cos[sr + d], sn = R.sin[sr + d];
+                            if ((d & 1) == 0) hv[m] = __hfma(tile_s[m * 128 + tidw + 1], __hneg(sn), __hmul(hv[m], c));
+                            else hv[m] = __hfma(tile_s[m * 128 + tidw - 1], sn, __hmul(hv[m], c));
+                        }
+                    }
+                }
+            }
+            float ssq[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                ssq[m] = 0.f;
+                if (col_ok && m < M) {
+                    mo.c[(size_t)m * mo.ldc + n_col] = hv[m];
+                    const float f = fmaxf(-65504.f, fminf(__half2float(hv[m]), 65504.f));
+                    ssq[m] = f * f;
+                    for (int t = 0; t < P.ex.num_scat; ++t) {
+                        const ScatterTarget& T = P.ex.scat[t];
+                        const int kp = T.invperm ? (int)__ldg(T.invperm + n_col) : n_col;
+                        const half o = T.scale ? __float2half_rn(f * __half2float(__ldg(T.scale + n_col))) : hv[m];
+                        T.xp[(size_t)(kp >> 3) * 64 + m * 8 + (kp & 7)] = o;
+                    }
+                }
+            }
+            if (P.ex.sumsq_out) {        // per-strip sum of squares of the stored rows, fixed reduction order
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], o);
+                    if (lane == 0) ssq_s[wq * 8 + m] = ssq[m];
+                }
+                bar_sync(3, 128);
+                if (tidw < 8) {
+                    const float t4 = (ssq_s[tidw] + ssq_s[8 + tidw]) + (ssq_s[16 + tidw] + ssq_s[24 + tidw]);
+                    P.ex.sumsq_out[(size_t)strip * 8 + tidw] = (tidw < MT) ? t4 : 0.f;
+                }
             }
         }
         __syncthreads();
@@ -632,7 +722,8 @@ int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_b
 static half* g_xp_scratch[64] = {nullptr};
 constexpr size_t TC_XP_BYTES_PER_MAT = (size_t)65536 * 16;      // K <= 65536, 16 B per k (8 token slots)
 
-int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue) {
+int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue,
+                   const GemvExtras* ex) {
     EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
     if (M <= 0) return 0;
     float* ws = nullptr;
@@ -652,20 +743,29 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     GemvParams P = {};
     P.num_mats = nm;
     P.KS = mats[0].w.KS;
+    const bool prepared = ex && ex->prepared;
+    if (ex) {
+        P.ex = *ex;
+        EXL2B_REQUIRE(M <= GEMV_MTOK, "fused epilogue extras need a single pass (rows %d > %d)", M, GEMV_MTOK);
+        if (ex->rope.mask) EXL2B_REQUIRE(ex->rope.head_dim > 0 && 128 % ex->rope.head_dim == 0 && ex->rope.sincos_size <= ex->rope.head_dim,
+                                         "fused RoPE needs head_dim to divide 128");
+        if (ex->sumsq_in) P.ex.sumsq_eps = norm_eps;
+    }
     long long units = 0;
     int strips = 0;
     for (int i = 0; i < nm; ++i) {
         EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_TC, "matrix is not in the tcgen05 layout");
         EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
-        EXL2B_REQUIRE(mats[i].x == mats[0].x && mats[i].ldx == mats[0].ldx, "fused matrices must share their input");
+        EXL2B_REQUIRE(prepared || (mats[i].x == mats[0].x && mats[i].ldx == mats[0].ldx), "fused matrices must share their input");
         P.mat[i] = mats[i];
         P.mat[i].unit_begin = (int)units;
         P.mat[i].strip_begin = strips;
-        P.mat[i].xp = g_xp_scratch[device] + (size_t)i * (TC_XP_BYTES_PER_MAT / sizeof(half));
+        if (prepared) EXL2B_REQUIRE(mats[i].xp, "prepared launch without an activation buffer");
+        else P.mat[i].xp = g_xp_scratch[device] + (size_t)i * (TC_XP_BYTES_PER_MAT / sizeof(half));
         units += (long long)mats[i].w.strips * P.KS;
         strips += mats[i].w.strips;
     }
-    if (norm_w) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
+    if (norm_w && !prepared) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
     if (epilogue != EPI_STORE) EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
     P.norm_w = norm_w;
     P.norm_eps = norm_eps;
@@ -706,7 +806,7 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     const long long seg_max = std::min((long long)P.KS, (units + grid - 1) / grid + 4);      // + group snapping slack
     P.tc_stage_bytes = stage_bytes;
     P.tc_act_bytes = (int)(seg_max * SLAB_K * 16);                                           // 16 B per k (8 token slots)
-    const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + 1023) / 1024) * 1024;
+    const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + GEMV_MTOK * 128 * 2 + 128 + 1023) / 1024) * 1024;
     P.tc_act_off = header;
     const size_t smem_total = (size_t)header + P.tc_act_bytes + (size_t)TC_WARPS * TC_STAGES * stage_bytes;
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "K range per CTA too large for shared memory (%zu bytes)", smem_total);
@@ -729,12 +829,15 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
         P.M = std::min(GEMV_MTOK, M - m0);
         P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
         for (int i = 0; i < nm; ++i) {
-            P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
+            if (!prepared) P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
             P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
         }
-        Q.x = mats[0].x + (size_t)m0 * mats[0].ldx;
-        Q.M = P.M;
-        EXL2B_CUDA(launch_pdl(tc_prep_kernel, dim3(GEMV_MTOK), dim3(1024), 0, stream, Q));
+        P.row0 = m0;
+        if (!prepared) {
+            Q.x = mats[0].x + (size_t)m0 * mats[0].ldx;
+            Q.M = P.M;
+            EXL2B_CUDA(launch_pdl(tc_prep_kernel, dim3(GEMV_MTOK), dim3(1024), 0, stream, Q));
+        }
         if (P.M == 1) {
             EXL2B_CUDA(launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
         } else {

@@ -561,14 +561,22 @@ int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_b
     return 0;
 }
 
-int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue);
+int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue,
+                   const GemvExtras* ex);
+
+bool gemv_supports_extras(const GemvMat* mats, int nm, int M) {
+    for (int i = 0; i < nm; ++i)
+        if (mats[i].w.layout != LAYOUT_TC) return false;
+    return M >= 1 && M <= GEMV_MTOK;
+}
 
 int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps,
-                int epilogue) {
+                int epilogue, const GemvExtras* ex) {
     EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
     EXL2B_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
     if (M <= 0) return 0;
-    if (mats[0].w.layout == LAYOUT_TC) return gemm_tc_launch(device, stream, mats, nm, M, norm_w, norm_eps, epilogue);
+    if (mats[0].w.layout == LAYOUT_TC) return gemm_tc_launch(device, stream, mats, nm, M, norm_w, norm_eps, epilogue, ex);
+    EXL2B_REQUIRE(!ex, "epilogue fusions are only implemented for the tcgen05 layout");
     DeviceWorkspace* dw = nullptr;
     int rc = ensure_workspace(device, &dw);
     if (rc) return rc;

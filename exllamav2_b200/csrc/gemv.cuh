@@ -25,6 +25,36 @@ struct GemvMat {
     int strip_begin; // filled by the launcher
 };
 
+// ---- optional fusions around a launch (tcgen05 path) --------------------------------------------------------------------
+// RoPE applied in the epilogue of the matrices selected by `mask` (cuda/rope.cu:10-123 arithmetic; needs 128 % head_dim == 0
+// so that a rotation partner lives in the same 128-column strip)
+struct RopeFuse {
+    const half* sin;
+    const half* cos;
+    const int32_t* past_lens;
+    int past_len, q_len, head_dim, sincos_size, neox;
+    unsigned mask;          // bit i: rotate mat[i]'s output
+};
+// A consumer of this launch's output: its activation buffer is filled directly from the epilogue, already permuted
+// into the consumer's row order, in the UMMA core-matrix layout, times the consumer's RMSNorm weight -- the consumer
+// launch then needs no prep kernel.  The RMSNorm's 1/rms is deferred: the producer leaves per-strip sums of squares
+// in `sumsq`, the consumer multiplies its fp32 result by rsqrt(sum / K + eps).
+struct ScatterTarget {
+    half* xp;
+    const uint16_t* invperm;    // consumer row of feature n (NULL: identity)
+    const half* scale;          // RMSNorm weight (NULL: none)
+};
+struct GemvExtras {
+    RopeFuse rope;                         // mask == 0: none
+    ScatterTarget scat[GEMV_MAX_MATS];
+    int num_scat;
+    float* sumsq_out;                      // [strips][8] or NULL
+    int prepared;                          // 1: mats[i].xp already hold the input (no prep launch)
+    const float* sumsq_in;                 // with prepared: per-strip sums of squares of the input rows, or NULL (no norm)
+    int sumsq_in_strips;
+    float sumsq_eps;
+};
+
 struct GemvParams {
     GemvMat mat[GEMV_MAX_MATS];
     int num_mats;
@@ -44,12 +74,16 @@ struct GemvParams {
     int tc_stage_bytes;    // tcgen05 kernel: bytes of one weight stage (largest group of one 32-column block)
     int tc_act_off;        // tcgen05 kernel: shared-memory offset of the staged activations
     int tc_act_bytes;      // tcgen05 kernel: capacity of the staged activations (16 B per k)
+    int row0;              // first token row of this pass (RoPE position bookkeeping)
+    GemvExtras ex;
 };
 
 // Launch one or more passes (8 tokens each) of the GEMV over `nm` matrices that share K and the input layout.
 // All matrices must live on `device`.  M may exceed 8 (extra passes re-read the weights, like the reference's
 // grid.y = ceil(M/4) does, cuda/q_gemm.cu:97).
 int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps,
-                int epilogue);
+                int epilogue, const GemvExtras* ex = nullptr);
+// can `ex` be honoured for these matrices / this row count?  (tcgen05 layout, one pass)
+bool gemv_supports_extras(const GemvMat* mats, int nm, int M);
 
 }  // namespace exl2b

@@ -327,6 +327,7 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
     v.gptq_scales = (const half*)d->gptq_scales;
     v.perm = d->q_perm;
     v.bias = (const half*)d->bias;
+    m->invperm = d->q_perm ? d->q_invperm : nullptr;
 
     std::vector<GroupInfo> ginfo;
     int gptq_gs = 0;
@@ -444,12 +445,27 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
     return 0;
 }
 
+namespace exl2b {
+int qmatrix_chain_buffers(QMatrix* m) {
+    if (m->xp_buf) return 0;
+    EXL2B_CUDA(cudaSetDevice(m->device));
+    const size_t xp_bytes = (size_t)m->v.K * 16, sq_bytes = ((size_t)m->v.K / 128 + 2) * 8 * sizeof(float);
+    EXL2B_CUDA(cudaMalloc(&m->xp_buf, xp_bytes));
+    EXL2B_CUDA(cudaMalloc(&m->sumsq_buf, sq_bytes));
+    EXL2B_CUDA(cudaMemset(m->xp_buf, 0, xp_bytes));
+    EXL2B_CUDA(cudaMemset(m->sumsq_buf, 0, sq_bytes));
+    return 0;
+}
+}  // namespace exl2b
+
 extern "C" int exl2b_qmatrix_destroy(exl2b_qmatrix_t h) {
     QMatrix* m = (QMatrix*)h;
     if (!m) return 0;
     cudaSetDevice(m->device);
     if (m->tables) cudaFree(m->tables);
     if (m->owned_packed) cudaFree(m->owned_packed);
+    if (m->xp_buf) cudaFree(m->xp_buf);
+    if (m->sumsq_buf) cudaFree(m->sumsq_buf);
     delete m;
     return 0;
 }

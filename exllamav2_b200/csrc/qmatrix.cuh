@@ -45,7 +45,12 @@ struct QMatrix {
     uint32_t bits_mask = 0;             // bit b set <=> some group uses b bits
     uint64_t packed_bytes = 0;
     std::vector<uint2> slab_tab_host;
+    const uint16_t* invperm = nullptr;  // q_invperm of the checkpoint (device), NULL = identity
+    half* xp_buf = nullptr;             // chained launches: this matrix's input, written by its producer's epilogue
+    float* sumsq_buf = nullptr;         //   and the producer's per-strip sums of squares (deferred RMSNorm)
 };
+// allocate xp_buf / sumsq_buf on first use (never inside a stream capture: call once eagerly first)
+int qmatrix_chain_buffers(QMatrix* m);
 
 inline uint32_t meta_group(uint32_t m) { return m & 0xFFFFu; }
 inline uint32_t meta_bits(uint32_t m) { return (m >> 16) & 0xFu; }

@@ -86,6 +86,18 @@ _sig("exl2b_qattn_forward_2", c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
 _sig("exl2b_qmlp_create", c_int, POINTER(_QMlpDesc), POINTER(c_void_p))
 _sig("exl2b_qmlp_destroy", c_int, c_void_p)
 _sig("exl2b_qmlp_forward", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p)
+_sig("exl2b_paged_attn_decode_q4", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p]))
+
+
+class _Chain(Structure):
+    _fields_ = [("consumers", c_void_p * 3), ("num_consumers", c_int), ("norm_weight", c_void_p)]
+
+
+_sig("exl2b_qattn_forward_1_ex", c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+     c_void_p, c_void_p, c_int, c_void_p)
+_sig("exl2b_qattn_forward_2_ex", c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(_Chain), c_void_p)
+_sig("exl2b_qmlp_forward_ex", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, POINTER(_Chain), c_void_p)
+_sig("exl2b_gemm_half_q_half_prepared", c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p)
 
 # Dummy tensor standing for None/NULL (ext.py:296 of the reference)
 none_tensor = torch.empty((1, 1), device="meta")
@@ -428,6 +440,58 @@ def q_mlp_forward_(q_mlp: int, x, loras=(), loras_temp=none_tensor):
 
 
 # names the reference's hot-path call sites use that this module provides
+
+def make_chain(consumers, norm_weight=None) -> "_Chain":
+    """Describe who reads a launch's output: `consumers` = q_handles of the matrices fed by it, `norm_weight` = the
+    RMSNorm weight they apply (include/exl2_b200.h exl2b_chain_t).  Keep the returned object (and norm_weight) alive."""
+    c = _Chain()
+    for i, hnd in enumerate(consumers):
+        c.consumers[i] = hnd
+    c.num_consumers = len(consumers)
+    c.norm_weight = _p(norm_weight)
+    c._keep = norm_weight
+    return c
+
+
+def q_attn_forward_1_ex(q_attn: int, x, batch_size: int, q_len: int, past_len: int, past_lens, q_temp, k_temp, v_temp, sin, cos,
+                        input_prepared: bool):
+    _check(lib.exl2b_qattn_forward_1_ex(q_attn, _p(x), batch_size, q_len, int(past_len), _p(past_lens), q_temp.data_ptr(),
+                                        k_temp.data_ptr(), v_temp.data_ptr(), _p(sin), _p(cos), int(input_prepared), _stream(q_temp)))
+
+
+def q_attn_forward_2_ex(q_attn: int, x, attn_output, batch_size: int, q_len: int, input_prepared: bool, chain=None):
+    _check(lib.exl2b_qattn_forward_2_ex(q_attn, x.data_ptr(), _p(attn_output), batch_size, q_len, int(input_prepared),
+                                        ctypes.byref(chain) if chain is not None else None, _stream(x)))
+
+
+def q_mlp_forward_ex(q_mlp: int, x, input_prepared: bool, chain=None):
+    temp_a, temp_b = _mlp_temps[q_mlp]
+    rows = x.numel() // x.shape[-1]
+    _check(lib.exl2b_qmlp_forward_ex(q_mlp, x.data_ptr(), rows, temp_a.data_ptr(), _p(temp_b), int(input_prepared),
+                                     ctypes.byref(chain) if chain is not None else None, _stream(x)))
+
+
+def gemm_half_q_half_prepared(b: int, c, has_norm: bool, norm_eps: float, clear: bool = True):
+    _check(lib.exl2b_gemm_half_q_half_prepared(b, c.data_ptr(), c.stride(0), c.shape[0], int(clear), int(has_norm),
+                                               float(norm_eps), _stream(c)))
+
+
+def paged_attn_decode_q4(q, k_new, v_new, k_cache, k_scales, v_cache, v_scales, cache_seqlens, block_table, out,
+                         softmax_scale: float, out_consumer: int = 0):
+    """Decode attention over the paged Q4 cache with quantise-and-append of the new rows (include/exl2_b200.h
+    exl2b_paged_attn_decode_q4).  q [B, q_len, H, hd]; k_new / v_new [B, q_len, KVH, hd]; caches uint8
+    [pages, page, KVH, hd/2] + fp16 scales [pages, page, KVH, hd/32]; out like q.  No reference counterpart as one op:
+    it replaces q_to_fp16_kv + flash_attn_with_kvcache + fp16_to_q_kv (attn.py:560-613)."""
+    B, q_len, H, hd = q.shape
+    KVH = k_new.shape[2]
+    for t in (q, k_new, v_new, out):
+        _dtype(_cuda(t, "attention operand"), torch.half, "attention operand")
+    _check(lib.exl2b_paged_attn_decode_q4(
+        _p(q), _p(k_new), _p(v_new), _p(k_cache), _p(k_scales), _p(v_cache), _p(v_scales),
+        _p(cache_seqlens), _p(block_table), _p(out), B, q_len, H, KVH, hd, k_cache.shape[1], block_table.shape[1],
+        float(softmax_scale), out_consumer or None, _stream(q)))
+
+
 HOT_PATH_EXPORTS = [
     "make_q_matrix", "free_q_matrix", "reconstruct", "gemm_half_q_half", "make_group_map",
     "rms_norm", "rms_norm_", "rope_", "fp16_to_q_kv", "q_to_fp16_kv",

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -140,7 +141,7 @@ class ExLlamaV2Decoder:
 
         def lin(K, N, plan, s):
             bits, prop, gs = plan
-            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s)
+            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K))
             self.weight_bytes += synthetic.algorithmic_bytes(w, 1)
             l = ExLlamaV2Linear(K, N, device=dev)
             l.load(w)
@@ -184,15 +185,36 @@ class ExLlamaV2Decoder:
         self.xn = torch.empty((B, hid), dtype=torch.half, device=dev)
         self.logits = torch.empty((B, cfg.vocab_size), dtype=torch.half, device=dev)
         self.graph = None
+        # True: attention reads the Q4 cache directly (one kernel per layer); False: the reference's sequence
+        # q_to_fp16_kv -> attention on the fp16 temp -> fp16_to_q_kv (three kernels + the temp round trip)
+        self.fused_attn = os.environ.get("EXL2B_REF_KV_SEQUENCE") is None
+        # producer epilogues feed consumer activation buffers (needs the default tcgen05 matrix layout)
+        self.chained = os.environ.get("EXL2B_NO_CHAIN") is None and not os.environ.get("EXL2B_LAYOUT", "").startswith("m")
+        for L in self.layers:
+            L.chain_attn = ext_c.make_chain([L.q_proj.q_handle, L.k_proj.q_handle, L.v_proj.q_handle], L.input_norm)
+            L.chain_mlp = ext_c.make_chain([L.gate.q_handle, L.up.q_handle], L.post_norm)
+        self.chain_head = ext_c.make_chain([self.lm_head.q_handle], self.final_norm)
 
     # -- one decoder step over `q_len` new tokens per sequence (q_len small; rows = B * q_len) --
     def _forward_tokens(self, x, q, k, v, attn_out, q_len: int):
         cfg, cache = self.cfg, self.cache
         B = self.batch_size
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        if self.chained and self.fused_attn and B * q_len <= 8:
+            return self._forward_tokens_chained(x, q, k, v, attn_out, q_len)
         for li, L in enumerate(self.layers):
+            if self.fused_attn and q_len <= 8:
+                # past_len = -1: positions come from cache_seqlens on the device (rope.cu:39-43)
+                ext_c.q_attn_forward_1(L.attn, x, B, q_len, -1, cache.cache_seqlens, q, k, v, self.sin, self.cos)
+                ext_c.paged_attn_decode_q4(q.view(B, q_len, H, hd), k.view(B, q_len, KVH, hd), v.view(B, q_len, KVH, hd),
+                                           cache.key_states[li], cache.key_scales[li], cache.value_states[li],
+                                           cache.value_scales[li], cache.cache_seqlens, cache.block_table,
+                                           attn_out.view(B, q_len, H, hd), 1.0 / math.sqrt(hd))
+                ext_c.q_attn_forward_2(L.attn, x, attn_out, B, q_len)
+                ext_c.q_mlp_forward_(L.mlp, x)
+                continue
             tk, tv = cache.get_kv_state(li)
-            # past_len = -1: positions come from cache_seqlens on the device (rope.cu:39-43)
             ext_c.q_attn_forward_1(L.attn, x, B, q_len, -1, cache.cache_seqlens, q, k, v, self.sin, self.cos)
             rc = _lib.exl2b_paged_attn_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), tk.data_ptr(), tv.data_ptr(),
                                               cache.cache_seqlens.data_ptr(), cache.block_table.data_ptr(), attn_out.data_ptr(),
@@ -205,8 +227,36 @@ class ExLlamaV2Decoder:
             ext_c.q_mlp_forward_(L.mlp, x)
         cache.cache_seqlens.add_(q_len)
 
+    def _forward_tokens_chained(self, x, q, k, v, attn_out, q_len: int, head: bool = False, gemv_only: bool = False):
+        """Same layer loop with every producer's epilogue feeding its consumer's activation buffer (include/exl2_b200.h
+        "chained launches"): 5 launches per layer -- QKV(+norm+rope), attention over the Q4 cache, O(+residual),
+        gate|up(+norm+act), down(+residual) -- and no stand-alone norm / rope / prep / cache kernels."""
+        cfg, cache = self.cfg, self.cache
+        B = self.batch_size
+        H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        n = len(self.layers)
+        for li, L in enumerate(self.layers):
+            ext_c.q_attn_forward_1_ex(L.attn, x, B, q_len, -1, cache.cache_seqlens, q, k, v, self.sin, self.cos, li > 0)
+            if not gemv_only:        # (bench.py's roofline loop replays exactly the GEMV launches, nothing else)
+                ext_c.paged_attn_decode_q4(q.view(B, q_len, H, hd), k.view(B, q_len, KVH, hd), v.view(B, q_len, KVH, hd),
+                                           cache.key_states[li], cache.key_scales[li], cache.value_states[li],
+                                           cache.value_scales[li], cache.cache_seqlens, cache.block_table,
+                                           attn_out.view(B, q_len, H, hd), 1.0 / math.sqrt(hd), L.o_proj.q_handle)
+            ext_c.q_attn_forward_2_ex(L.attn, x, attn_out, B, q_len, True, L.chain_mlp)
+            if li + 1 < n:
+                nxt = self.layers[li + 1].chain_attn
+            else:
+                nxt = self.chain_head if head else None
+            ext_c.q_mlp_forward_ex(L.mlp, x, True, nxt)
+        if not gemv_only:
+            cache.cache_seqlens.add_(q_len)
+
     def _decode_step(self):
         torch.index_select(self.embed, 0, self.ids.view(-1), out=self.x.view(self.batch_size, -1))
+        if self.chained and self.fused_attn and self.batch_size <= 8:
+            self._forward_tokens_chained(self.x, self.q, self.k, self.v, self.attn_out, 1, head=True)
+            ext_c.gemm_half_q_half_prepared(self.lm_head.q_handle, self.logits, True, self.cfg.norm_eps)
+            return
         self._forward_tokens(self.x, self.q, self.k, self.v, self.attn_out, 1)
         ext_c.rms_norm(self.x.view(self.batch_size, -1), self.final_norm, self.xn, self.cfg.norm_eps)
         ext_c.gemm_half_q_half(self.xn, self.lm_head.q_handle, self.logits, False)

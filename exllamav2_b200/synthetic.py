@@ -32,7 +32,10 @@ def group_plan(K: int, bits, bits_prop, group_size) -> list[tuple[int, int]]:
 
 
 def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, device="cuda:0", seed: int = 0,
-                perm: bool = True) -> dict:
+                perm: bool = True, weight_std: float | None = None) -> dict:
+    """Random EXL2 tensors.  weight_std: target standard deviation of the dequantised weights (1/sqrt(K) keeps a
+    random-init network's activations O(1), like a trained checkpoint's ~0.02 at K = 4096); None: scale_max in
+    [0.5, 4) stored units, i.e. weights of magnitude ~5 (fine for single-matrix tests, overflows fp16 in a deep stack)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     plan = group_plan(K, list(bits), list(bits_prop), group_size)
@@ -50,6 +53,12 @@ def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, dev
         "q_groups": q_groups.to(device),
         "q_invperm": (torch.randperm(K, device=device, generator=gen) if perm else torch.arange(K, device=device)).to(torch.int32),
     }
+    if weight_std is not None:
+        # std of (q - 2^(b-1)) for uniform q is 2^b / sqrt(12); E[(s+1)^2] for a uniform 4-bit scale nibble is 93.5;
+        # the stored q_scale_max carries a factor 256 (the loader multiplies by 1/256, ext.py:336 of the reference)
+        b = torch.tensor([p[0] for p in plan], dtype=torch.float32, device=device)
+        jitter = torch.rand((G,), device=device, generator=gen) * 0.6 + 0.7
+        w["q_scale_max"] = (256.0 * weight_std / ((2.0 ** b) / math.sqrt(12.0) * 93.5) * jitter).half()
     w["q_perm"] = torch.argsort(w["q_invperm"]).to(torch.int)
     return w
 

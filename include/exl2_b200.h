@@ -161,6 +161,41 @@ int exl2b_paged_attn_decode(const uint16_t* q, const uint16_t* k_new, const uint
                             int batch, int q_len, int num_heads, int num_kv_heads, int head_dim, int page_size,
                             int pages_per_seq, float softmax_scale, exl2b_stream_t stream);
 
+/* Decode attention straight over the Q4 cache (replaces the reference's per-layer sequence q_to_fp16_kv ->
+ * flash_attn_with_kvcache -> fp16_to_q_kv, attn.py:560-613 + cache.py:472-556): quantises the q_len new K/V rows with
+ * the fp16_to_q_kv arithmetic, appends them to the paged Q4 cache at [seqlen, seqlen+q_len) and attends causally over
+ * the stored 4-bit values.  k/v_cache uint8 [pages,page_size,KVH,hd/2], k/v_scales fp16 [pages,page_size,KVH,hd/32];
+ * 1 <= q_len <= 8; head_dim 64 or 128. */
+int exl2b_paged_attn_decode_q4(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint8_t* k_cache,
+                               uint16_t* k_scales, uint8_t* v_cache, uint16_t* v_scales, const int32_t* cache_seqlens,
+                               const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
+                               int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
+                               exl2b_qmatrix_t out_consumer, exl2b_stream_t stream);
+
+/* ---- chained launches (no reference counterpart; the reference runs norm / projection / rope / activation as separate
+ * kernels, q_attn.cu:153-345, q_mlp.cu:78-236).  A producer's epilogue can write its output straight into the
+ * activation buffer of the matrices that consume it -- permuted through their q_invperm, in the tensor-core operand
+ * layout, pre-multiplied by the RMSNorm weight they apply -- together with per-strip sums of squares; the consumer
+ * launch (`input_prepared` = 1) then starts without a prep kernel and applies 1/rms to its fp32 result.
+ * Valid for rows <= 8 (decode) and the default (tcgen05) matrix layout; the calls fail otherwise.
+ * `out_consumer` of exl2b_paged_attn_decode_q4 is the same mechanism for the attention output (o_proj). */
+typedef struct {
+    exl2b_qmatrix_t consumers[3];   /* matrices whose INPUT is this launch's output (e.g. the next block's q, k, v) */
+    int num_consumers;
+    const uint16_t* norm_weight;    /* RMSNorm weight the consumers apply to that input, or NULL */
+} exl2b_chain_t;
+int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int batch, int q_len, int past_len, const int32_t* past_lens,
+                             uint16_t* q, uint16_t* k, uint16_t* v, const uint16_t* sin, const uint16_t* cos,
+                             int input_prepared, exl2b_stream_t stream);
+int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint16_t* attn_out, int batch, int q_len, int input_prepared,
+                             const exl2b_chain_t* next, exl2b_stream_t stream);
+int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b, int input_prepared,
+                          const exl2b_chain_t* next, exl2b_stream_t stream);
+/* gemm_half_q_half on an input prepared by a chained producer (lm_head after the last MLP; has_norm: apply 1/rms) */
+int exl2b_gemm_half_q_half_prepared(exl2b_qmatrix_t h, uint16_t* c, int ldc, int m, int clear, int has_norm, float norm_eps,
+                                    exl2b_stream_t stream);
+int exl2b_qmatrix_chain_target(exl2b_qmatrix_t h, uint16_t** xp, const uint16_t** invperm);
+
 #ifdef __cplusplus
 }
 #endif

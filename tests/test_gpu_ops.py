@@ -175,6 +175,68 @@ def test_kv_q4_paged():
             assert np.array_equal(cases.u16(ko[p, tok % page].cpu().numpy().reshape(1, -1)), cases.u16(want))
 
 
+
+@pytest.mark.parametrize("H,KVH,hd,q_len,seqlens", [
+    (8, 8, 128, 1, [300, 0]),          # crosses a page; an empty sequence
+    (8, 2, 64, 3, [17, 255]),          # GQA, several new rows, append runs over a page end
+    (4, 4, 128, 8, [511, 5]),
+])
+def test_paged_attn_decode_q4(H, KVH, hd, q_len, seqlens):
+    """Fused Q4 attention == oracle: pack the new rows (fp16_to_q_kv arithmetic, bit-exact cache contents), then
+    softmax(q K^T / sqrt(hd)) V in fp64 over the oracle-dequantised cached rows plus the new rows in fp16 -- the step
+    that appends a row attends it unquantised, as flash_attn_with_kvcache does in the reference (attn.py:602-621).
+    Tolerance 2e-3 relative L2 (the reference pipeline rounds the dequantised K/V to fp16; this kernel keeps fp32)."""
+    from exllamav2_b200 import ext as ext_c
+    page, pps = 256, 3
+    B = len(seqlens)
+    rng = np.random.default_rng(31)
+    pages_total = B * pps + 1
+    block_table = rng.permutation(pages_total)[:B * pps].reshape(B, pps).astype(np.int32)
+    past_k = rng.normal(0, 1, size=(pages_total, page, KVH, hd)).astype(np.float16)
+    past_v = rng.normal(0, 1, size=(pages_total, page, KVH, hd)).astype(np.float16)
+    kq0, ks0 = oracle.kv_pack_q4(past_k)
+    vq0, vs0 = oracle.kv_pack_q4(past_v)
+    q = rng.normal(0, 1, size=(B, q_len, H, hd)).astype(np.float16)
+    kn = rng.normal(0, 1, size=(B, q_len, KVH, hd)).astype(np.float16)
+    vn = rng.normal(0, 1, size=(B, q_len, KVH, hd)).astype(np.float16)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    kq, ks, vq, vs = t(kq0.copy()), t(ks0.copy()), t(vq0.copy()), t(vs0.copy())
+    out = torch.zeros((B, q_len, H, hd), dtype=torch.half, device=DEV)
+    sl = t(np.array(seqlens, dtype=np.int32))
+    ext_c.paged_attn_decode_q4(t(q), t(kn), t(vn), kq, ks, vq, vs, sl, t(block_table), out, 1.0 / np.sqrt(hd))
+    torch.cuda.synchronize()
+    kq1, ks1, vq1, vs1 = kq.cpu().numpy(), ks.cpu().numpy(), vq.cpu().numpy(), vs.cpu().numpy()
+    got = out.cpu().numpy()
+    # 1. the appended rows are exactly what fp16_to_q_kv stores; nothing else moved
+    want_kq, want_ks, want_vq, want_vs = kq0.copy(), ks0.copy(), vq0.copy(), vs0.copy()
+    nkq, nks = oracle.kv_pack_q4(kn)
+    nvq, nvs = oracle.kv_pack_q4(vn)
+    for b in range(B):
+        for i in range(q_len):
+            pos = seqlens[b] + i
+            pg = block_table[b, pos // page]
+            want_kq[pg, pos % page], want_ks[pg, pos % page] = nkq[b, i], nks[b, i]
+            want_vq[pg, pos % page], want_vs[pg, pos % page] = nvq[b, i], nvs[b, i]
+    assert np.array_equal(kq1, want_kq) and np.array_equal(vq1, want_vq)
+    assert np.array_equal(cases.u16(ks1), cases.u16(want_ks)) and np.array_equal(cases.u16(vs1), cases.u16(want_vs))
+    # 2. attention over the dequantised cache
+    kd = oracle.kv_unpack_q4(kq1, ks1).astype(np.float64)
+    vd = oracle.kv_unpack_q4(vq1, vs1).astype(np.float64)
+    group = H // KVH
+    for b in range(B):
+        for i in range(q_len):
+            n = seqlens[b] + i + 1
+            rows = [(block_table[b, p // page], p % page) for p in range(seqlens[b])]
+            for h in range(H):
+                K = np.stack([kd[pg, r, h // group] for pg, r in rows] + [kn[b, j, h // group].astype(np.float64) for j in range(i + 1)])
+                V = np.stack([vd[pg, r, h // group] for pg, r in rows] + [vn[b, j, h // group].astype(np.float64) for j in range(i + 1)])
+                s = K @ q[b, i, h].astype(np.float64) / np.sqrt(hd)
+                pr = np.exp(s - s.max())
+                ref = (pr / pr.sum()) @ V
+                err = oracle.rel_l2(got[b, i, h].astype(np.float64), ref)
+                assert err < 2e-3, (b, i, h, err)
+
+
 # ---- fused blocks ---------------------------------------------------------------------------------------------------
 
 def _lin(w_np, K, N):

@@ -1,0 +1,43 @@
+"""Per-launch timeline of the dequant-GEMM launches inside a real (graph-replayed) decode step: for each launch the
+earliest CTA start / latest CTA end (globaltimer, ns) and CTA 0's phase stamps.  Diagnostics only."""
+import ctypes, sys, json
+import torch
+sys.path.insert(0, ".")
+from exllamav2_b200 import ext as ext_c
+from exllamav2_b200.model import ExLlamaV2Decoder, PRESETS
+
+dev = "cuda:0"
+layers = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+cfg = PRESETS["llama2-7b-4.0bpw"]()
+cfg.num_layers = layers
+dec = ExLlamaV2Decoder(cfg, dev, seed=0, batch_size=1, cache_len=1024)
+g = torch.Generator().manual_seed(0)
+dec.prefill(torch.randint(0, cfg.vocab_size, (1, 128), generator=g).to(dev))
+ext_c.lib.exl2b_debug_set.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+stamps = torch.zeros((64, 32), dtype=torch.int64, device=dev)
+dec._decode_step(); torch.cuda.synchronize()
+ext_c.lib.exl2b_debug_set(0, stamps.data_ptr(), 0)
+dec.capture()                      # slots are assigned at capture: one per GEMM launch, in order
+ext_c.lib.exl2b_debug_set(0, None, 0)
+ids = torch.zeros((1, 1), dtype=torch.long, device=dev)
+for _ in range(3):
+    dec.decode(ids)
+torch.cuda.synchronize()
+stamps.zero_(); stamps[:, 6] = 2**62
+dec.decode(ids); torch.cuda.synchronize()
+st = stamps.cpu().tolist()
+n = 4 * layers + 1
+names = ["qkv", "o", "gateup", "down"]
+t0 = st[0][6]
+# the warm-up step in capture() used the first n slots; the captured graph the next n
+rows = [r for r in st if r[6] < 2**62]
+print("launches with stamps:", len(rows))
+prev_end = None
+for i, r in enumerate(rows):
+    nm = names[i % 4] if i < 4 * layers else "head"
+    gs, ge = r[6] - rows[0][6], r[7] - rows[0][6]
+    c = [x - rows[0][6] if x else None for x in r[0:6]]
+    print(f"{i:3d} {nm:7s} grid {gs/1e3:8.2f} -> {ge/1e3:8.2f} us  dur {(ge-gs)/1e3:6.2f}  gap_from_prev_end {((gs-prev_end)/1e3 if prev_end is not None else 0):6.2f}  cta0 "
+          + " ".join("   -  " if x is None else f"{x/1e3:7.2f}" for x in c))
+    prev_end = ge
+print("step span us", (rows[-1][7] - rows[0][6]) / 1e3)
