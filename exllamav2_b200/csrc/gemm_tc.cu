@@ -33,15 +33,15 @@ namespace exl2b {
 
 constexpr int TC_THREADS = 256;
 constexpr int TC_WARPS = 8;
-constexpr int TC_STAGES = 4;                      // stage = one group (<= 4 slabs) of one 32-column block; size set per launch
+constexpr int TC_MAX_STAGES = 4;                  // stage = one group (<= 4 slabs) of one 32-column block; count + size set per launch
 constexpr int TC_NTOK = 16;                       // UMMA N; tokens 8..15 alias tokens 0..7 (SBO = 0), only 8 are real
-constexpr int TC_SMEM_BARS = (TC_WARPS * TC_STAGES + 4) * 8;
+constexpr int TC_ACT_STAGE = 2048;                // activations of one group: 128 k x 16 B (8 token slots)
+constexpr int TC_NBARS = TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 2 * 3 + 2 * 2;   // weights | act | A free | D ready
+constexpr int TC_SMEM_BARS = TC_NBARS * 8;
 constexpr int TC_SMEM_MISC = 128;                 // tmem base, rstd[8], flag
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_COL_ONES = 0;                    // 8 columns: all-ones A tile (K = 16)
-constexpr int TC_COL_OFFS = 8;                    // 8 columns: two-offset tile of the EXL2 4-bit unpack (+ zero point)
-constexpr int TC_COL_WG = 16;                     // per WG: A 64 cols | D 16 | D2 16
-constexpr int TC_COLS_PER_WG = 96;
+constexpr int TC_A_BUFS = 3;                      // per WG: 3 A buffers of 32 columns (2 slabs = 64 k each) ...
+constexpr int TC_COLS_PER_WG = 128;               //         ... + 2 accumulators of 16 columns
 constexpr int TC_RED_FLOATS = GEMV_MTOK * 128;    // workspace floats per (strip, contributor)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -184,25 +184,34 @@ __device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uin
     }
 }
 
-// unpack `nslab` slabs of this warp's block (contiguous at sp) into the WG's A buffer: 16 TMEM columns per slab
-template <int BITS, int MODE>    // MODE 0: exact (q - zp), 1: 4-bit two-offset form, 2: 4-bit uniform-offset form (GPTQ)
-__device__ __forceinline__ void tc_dequant_slab(const uint8_t* sp, int i, int lane, uint32_t a_taddr) {
+// 4-bit fields, exact: two-offset extraction (4 LOP3 + 1 SHF per 8 weights on the ALU pipe) and the offset + zero point
+// removed by one HADD2 per pair on the otherwise idle FMA pipe.  c0 = -(1024 + zero), c1 = -(64 + zero) as half2 bits;
+// EXL2: zero = 8 (qdq_4.cuh:34-60), GPTQ: zero = z + 1 per (group, column) (q_gemm_kernel_gptq.cuh:167-172).
+__device__ __forceinline__ void tc_dequant4(const uint32_t* mw, uint32_t c0, uint32_t c1, uint32_t* A) {
+    const uint32_t m0 = 0x000f000fu, g0 = 0x64006400u, m1 = 0x00f000f0u, g1 = 0x54005400u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = mw[w], y = x >> 8;
+        A[w * 4 + 0] = h2add_bits(and_or(x, m0, g0), c0);
+        A[w * 4 + 1] = h2add_bits(and_or(x, m1, g1), c1);
+        A[w * 4 + 2] = h2add_bits(and_or(y, m0, g0), c0);
+        A[w * 4 + 3] = h2add_bits(and_or(y, m1, g1), c1);
+    }
+}
+// unpack slab i of this warp's block stage (contiguous at sp) into 16 TMEM columns at a_taddr
+template <int BITS>
+__device__ __forceinline__ void tc_dequant_slab(const uint8_t* sp, int i, int lane, uint32_t a_taddr, uint32_t c0, uint32_t c1) {
     uint32_t mw[8], ew[2], A[16];
     tc_load_words<BITS>(sp + i * block_bytes(BITS), lane, mw, ew);
-    if constexpr (MODE == 1) dequant_block_4bit_offset2(mw, A);
-    else if constexpr (MODE == 2) dequant_block_4bit_offset(mw, A);
+    if constexpr (BITS == 4) tc_dequant4(mw, c0, c1, A);
     else dequant_block_exl2<BITS>(mw, ew, A);
-    tmem_st16(a_taddr + i * 16, A);
+    tmem_st16(a_taddr, A);
 }
-template <int BITS, int MODE>
-__device__ __forceinline__ void tc_dequant_group(const uint8_t* sp, int nslab, int lane, uint32_t a_taddr) {
-    if (nslab == 4) {            // the common case (128-row groups): straight-line code, slabs interleave freely
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tc_dequant_slab<BITS, MODE>(sp, i, lane, a_taddr);
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < nslab; ++i) tc_dequant_slab<BITS, MODE>(sp, i, lane, a_taddr);
-    }
+// one chunk = slabs [s0, s0 + nsl) of the stage, nsl <= 2, into one A buffer
+template <int BITS>
+__device__ __forceinline__ void tc_dequant_chunk(const uint8_t* sp, int s0, int nsl, int lane, uint32_t a_taddr, uint32_t c0, uint32_t c1) {
+    tc_dequant_slab<BITS>(sp, s0, lane, a_taddr, c0, c1);
+    if (nsl == 2) tc_dequant_slab<BITS>(sp, s0 + 1, lane, a_taddr + 16, c0, c1);
 }
 
 // ---- activation prep: RMSNorm + q_perm gather + UMMA core-matrix layout, once per launch ------------------------------
@@ -274,12 +283,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     griddep_launch_dependents();
     TC_STAMP(0);
 
-    // shared memory: [barriers][misc][WG1 totals] | [activations = UMMA B operand] | [8 weight rings]
+    // shared memory: [barriers][misc][WG1 totals][fp16 tile][ssq] | [2 activation rings] | [8 weight rings]
     const uint32_t smem0 = smem_addr(smem);
-    const int stage_bytes = P.tc_stage_bytes;
-    const uint32_t bars = smem0 + warp * TC_STAGES * 8;
-    const uint32_t bar_mma = smem0 + TC_WARPS * TC_STAGES * 8 + wg * 8;
-    const uint32_t bar_act = smem0 + TC_WARPS * TC_STAGES * 8 + 16;
+    const int stage_bytes = P.tc_stage_bytes, NS = P.tc_stages;
+    const uint32_t wbar = smem0 + warp * TC_MAX_STAGES * 8;                                   // my weight stages
+    const uint32_t abar = smem0 + (TC_WARPS * TC_MAX_STAGES + wg * TC_MAX_STAGES) * 8;          // my WG's activation stages
+    const uint32_t barA = smem0 + (TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + wg * 3) * 8;  // A buffer free (its MMAs retired)
+    const uint32_t barD = smem0 + (TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 6 + wg * 2) * 8;   // accumulator complete
     uint8_t* misc = smem + TC_SMEM_BARS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
     int* flag_s = reinterpret_cast<int*>(misc + 64);
@@ -287,18 +297,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [8][128] WG1 totals
     half* tile_s = reinterpret_cast<half*>(comb_s + GEMV_MTOK * 128);   // [8][128] fp16 outputs (RoPE partner exchange)
     float* ssq_s = reinterpret_cast<float*>(tile_s + GEMV_MTOK * 128);  // [4][8] per-warp sums of squares
-    const uint32_t act_a = smem0 + P.tc_act_off;
-    const int ring_off = P.tc_act_off + P.tc_act_bytes;
-    uint8_t* ring_p = smem + ring_off + warp * TC_STAGES * stage_bytes;
-    const uint32_t ring = smem0 + ring_off + warp * TC_STAGES * stage_bytes;
+    const uint32_t act_ring = smem0 + P.tc_act_off + wg * NS * TC_ACT_STAGE;
+    const int ring_off = P.tc_act_off + 2 * NS * TC_ACT_STAGE;
+    uint8_t* ring_p = smem + ring_off + warp * NS * stage_bytes;
+    const uint32_t ring = smem0 + ring_off + warp * NS * stage_bytes;
     const int M = P.M, KS = P.KS;
 
-    // ---- one-time setup: barriers, TMEM, constant A tiles ----
+    // ---- one-time setup: barriers, TMEM ----
     if (lane == 0) {
+        for (int st = 0; st < NS; ++st) mbar_init(wbar + 8 * st, 1);
+        if (wq == 0) {
+            for (int st = 0; st < NS; ++st) mbar_init(abar + 8 * st, 1);
 #pragma unroll
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(bars + 8 * s, 1);
-        if (wq == 0) mbar_init(bar_mma, 1);
-        if (warp == 0) mbar_init(bar_act, 1);
+            for (int i = 0; i < 3; ++i) mbar_init(barA + 8 * i, 1);
+            mbar_init(barD, 1);
+            mbar_init(barD + 8, 1);
+        }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
@@ -307,28 +321,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const uint32_t t_ones = tmem_base + TC_COL_ONES, t_offs = tmem_base + TC_COL_OFFS;
-    const uint32_t t_a = tmem_base + TC_COL_WG + wg * TC_COLS_PER_WG, t_d = t_a + 64, t_d2 = t_a + 80;
-    if (wg == 0) {
-        // all-ones tile (GPTQ: sum_k a[k]) and the two-offset tile of the EXL2 4-bit unpack incl. its zero point:
-        // k-pairs alternate (1024 + 8), (64 + 8)  -> D2 = sum_k a[k] * (offset_k + 8)
-        uint32_t r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = 0x3C003C00u;
-        tmem_st8(t_ones + lane_sel, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = h2_const_int(offset2_of_pair(j) + 8);
-        tmem_st8(t_offs + lane_sel, r);
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    const uint32_t t_a = tmem_base + wg * TC_COLS_PER_WG, t_d = t_a + TC_A_BUFS * 32;   // A: 3 x 32 columns, D: 2 x 16
 
     const unsigned U = (unsigned)P.total_units, G = gridDim.x;
     const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
 
-    uint32_t phases = 0, mma_phase = 0, act_phase = 0;
+    uint32_t wphase = 0, aphase = 0, phaseA = 0, phaseD = 0;     // parity bits per barrier
+    uint32_t ab = 0, a_uses = 0, dsel = 0;                        // A buffer / accumulator rotation of this WG (across segments)
     bool waited = false;
     auto after_wait = [&]() {       // first point where the previous kernel's output may be read
         if (P.ex.sumsq_in) {        // warp m: 1/rms of token m, strips summed in a fixed order
@@ -339,6 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             if (lane == 0) rstd_s[warp] = rsqrtf(sum / (float)(KS * SLAB_K) + P.ex.sumsq_eps);
         }
     };
+
     int u = u0;
     while (u < u1) {
         int mi = 0;
@@ -348,191 +348,216 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int local = u - mt.unit_begin;
         const int strip = local / KS, ks_a = local - strip * KS;
         const int seg = min(KS - ks_a, u1 - u);
-        // snap the slab range to group boundaries (every CTA applies the same rule, so ranges still tile the strip)
+        // snap the slab range to group boundaries (every CTA applies the same rule, so ranges still tile the strip);
+        // WG0 takes the first half of the range's groups, WG1 the second: two contiguous streams per CTA
         const int ks0 = tc_group_start(w, ks_a), ks1 = tc_group_start(w, ks_a + seg);
+        const int ksm = tc_group_start(w, ks0 + ((ks1 - ks0 + 1) >> 1));
+        const int my0 = wg ? ksm : ks0, my1 = wg ? ks1 : ksm;
         const int n_col = strip * 128 + tidw;                                  // this thread's output column
+        const bool col_live = n_col < w.N;
         const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
+        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(mt.xp);
+        const int nreg = w.num_regions;
 
-        auto group_len = [&](int ks) {          // slabs in the group starting at ks
-            const int r = tc_region_of(w, ks);
-            return min(1 << w.reg[r].spg_log2, tc_region_end(w, r) - ks);
-        };
-        int g_first = ks0;
-        if (wg == 1 && g_first < ks1) g_first += group_len(g_first);
+        // Group cursors: position + the current region's parameters in registers, so that stepping to the next group
+        // is a handful of integer ops; the kernel-parameter region table is only read when a region boundary is crossed.
+        //   C: the group being unpacked;   F: the next group to request (weights + activations), NS groups ahead
+        int c_ks = my0, c_r = tc_region_of(w, min(my0, KS - 1));
+        int c_bits = w.reg[c_r].bits, c_spg = 1 << w.reg[c_r].spg_log2, c_end = tc_region_end(w, c_r);
+        int c_grp = w.reg[c_r].group_base + ((my0 - w.reg[c_r].ks_begin) >> w.reg[c_r].spg_log2);
+        int f_ks = c_ks, f_r = c_r, f_bits = c_bits, f_spg = c_spg, f_end = c_end;
+        uint32_t f_off = w.reg[c_r].off_base + (uint32_t)(my0 - w.reg[c_r].ks_begin) * (uint32_t)block_bytes(c_bits);
+        int f_stage = 0, cstage = 0;
 
-        // ---- producer: this warp's block stream, one group per stage (weights never depend on a previous kernel) ----
-        int fetch_ks = g_first, fstage = 0, cstage = 0;
-        auto issue = [&]() {
-            const int r = tc_region_of(w, fetch_ks);
-            const QRegion& R = w.reg[r];
-            const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - fetch_ks);
-            const uint32_t bytes = (uint32_t)ns * block_bytes(R.bits);
+        // request group F's weights (every warp: its own block) and, optionally, its activations (the WG's first warp)
+        auto issue = [&](bool weights, bool acts) {
+            const int ns = min(f_spg, f_end - f_ks);
+            const uint32_t wbytes = (uint32_t)ns * (uint32_t)block_bytes(f_bits);
             if (elect_one()) {
-                mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
-                bulk_copy_g2s(ring + fstage * stage_bytes, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * block_bytes(R.bits),
-                              bytes, bars + 8 * fstage);
+                if (weights) {
+                    mbar_arrive_expect_tx(wbar + 8 * f_stage, wbytes);
+                    bulk_copy_g2s(ring + f_stage * stage_bytes, gsrc + f_off, wbytes, wbar + 8 * f_stage);
+                }
+                if (acts && wq == 0) {
+                    mbar_arrive_expect_tx(abar + 8 * f_stage, (uint32_t)ns * SLAB_K * 16);
+                    bulk_copy_g2s(act_ring + f_stage * TC_ACT_STAGE, asrc + (size_t)f_ks * SLAB_K * 16, (uint32_t)ns * SLAB_K * 16,
+                                  abar + 8 * f_stage);
+                }
             }
-            int nk = fetch_ks + ns;                       // skip the other WG's group
-            if (nk < ks1) nk += group_len(nk);
-            fetch_ks = nk;
-            fstage = (fstage + 1 == TC_STAGES) ? 0 : fstage + 1;
+            f_ks += ns;
+            f_off += wbytes;
+            f_stage = (f_stage + 1 == NS) ? 0 : f_stage + 1;
+            if (f_ks >= f_end && f_r + 1 < nreg) {
+                ++f_r;
+                f_bits = w.reg[f_r].bits;
+                f_spg = 1 << w.reg[f_r].spg_log2;
+                f_end = tc_region_end(w, f_r);
+                f_off = w.reg[f_r].off_base;
+            }
         };
+        // prologue: the first NS groups' weights (they never depend on a previous kernel); their activations follow after
+        // griddepcontrol.wait, requested by re-walking the same groups with a scratch copy of the cursor
+        int primed = 0;
 #pragma unroll 1
-        for (int s = 0; s < TC_STAGES && fetch_ks < ks1; ++s) issue();
+        for (; primed < NS && f_ks < my1; ++primed) issue(true, false);
         TC_STAMP(1);
 
-        // ---- the WG pipeline over its groups ----
+        // ---- the WG pipeline.  Per chunk (<= 2 slabs = 64 k): unpack -> tcgen05.st into a free A buffer -> WG barrier ->
+        //      one lane issues the chunk's MMAs and commits to "A buffer free"; the group's last chunk also commits to
+        //      "accumulator complete".  The accumulator of group g is read back (tcgen05.ld, scaled, added) only after
+        //      group g+1's MMAs have been issued, so the tensor core and the unpack overlap.
         float tot[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) tot[m] = 0.f;
-        bool pending = false, act_issued = false;
-        int pend_mode = 0;               // 0: exact unpack, 1: EXL2 4-bit two-offset (D - D2), 2: GPTQ (D - (64 + z + 1) * S)
-        uint32_t pend_word = 0;          // raw q_scale / qzeros word of the pending group (decoded only when consumed:
+        bool pending = false, act_started = false;
+        uint32_t pend_d = 0;             // accumulator index of the pending (issued, not yet read back) group
+        uint32_t pend_word = 0;          // raw q_scale word / GPTQ scale of the pending group (decoded only when drained:
         half pend_h = __float2half(0.f); //   the SM issues in order, so touching a load result early stalls the warp)
+        uint32_t zw_next = 0;            // GPTQ: qzeros word of the NEXT group (needed at unpack time, so fetched a group ahead)
+        if (w.is_gptq && col_live && c_ks < my1) zw_next = __ldg(w.qzeros + (size_t)c_grp * (w.N >> 3) + (n_col >> 3));
 
-        auto drain = [&]() {       // read back the previous group's accumulator, apply its scale
-            mbar_wait(bar_mma, mma_phase);
-            mma_phase ^= 1u;
+        auto drain = [&]() {       // accumulator of the previous group -> running totals; its stage gets the next request
+            const uint32_t d = pend_d;
+            mbar_wait(barD + 8 * d, (phaseD >> d) & 1u);
+            phaseD ^= 1u << d;
             tc_fence_after();
-            float pend_scale = 0.f, pend_coff = 0.f;
-            if (n_col < w.N) {
-                const int nib = (int)((pend_word >> ((n_col & 7) * 4)) & 15u);
+            float pend_scale = 0.f;
+            if (col_live) {
                 if (!w.is_gptq) {
+                    const int nib = (int)((pend_word >> ((n_col & 7) * 4)) & 15u);
                     pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), pend_h));    // qdq_util.cuh:24-30
-                    pend_coff = pend_mode == 1 ? 1.f : 0.f;
                 } else {
                     pend_scale = __half2float(pend_h);
-                    pend_coff = (float)(OFFSET4 + nib + 1);                                              // zero + 1
                 }
             }
-            float d[MT], d2[MT];
-            if constexpr (MT == 1) {
-                tmem_ld1(t_d + lane_sel, d[0]);
-                d2[0] = 0.f;
-                if (pend_mode) tmem_ld1(t_d2 + lane_sel, d2[0]);
-            } else {
-                tmem_ld8(t_d + lane_sel, d);
-                if (pend_mode) tmem_ld8(t_d2 + lane_sel, d2);
-                else {
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) d2[m] = 0.f;
-                }
-            }
+            float dd[MT];
+            if constexpr (MT == 1) tmem_ld1(t_d + d * 16 + lane_sel, dd[0]);
+            else tmem_ld8(t_d + d * 16 + lane_sel, dd);
             tmem_wait_ld();
 #pragma unroll
-            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, fmaf(-pend_coff, d2[m], d[m]), tot[m]);
+            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m], tot[m]);
             tc_fence_before();
+            if (f_ks < my1) issue(true, true);       // the drained group's MMAs have retired: both of its stages are free
         };
 
-        int gk = g_first;
-        int gi_dbg = 0;
-#define TC_GSTAMP(j) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0 && gi_dbg < 3) P.dbg[8 + gi_dbg * 6 + (j)] = tc_gtimer(); } while (0)
-        while (gk < ks1) {
-            TC_GSTAMP(0);
-            const int r = tc_region_of(w, gk);
-            const QRegion& R = w.reg[r];
-            const int bits = R.bits;
-            const int ns = min(1 << R.spg_log2, tc_region_end(w, r) - gk);
-            const int grp = R.group_base + ((gk - R.ks_begin) >> R.spg_log2);
+        while (c_ks < my1) {
+            const int bits = c_bits;
+            const int ns = min(c_spg, c_end - c_ks);
+            const int grp = c_grp;
 
-            // (a) this group's scale / zero for my column: requested now, decoded when the group is drained
-            const int mode = (bits == 4) ? (w.is_gptq ? 2 : 1) : 0;
+            // (a) this group's scale for my column: requested now, decoded when the group is drained
             uint32_t cur_word = 0;
             half cur_h = __float2half(0.f);
-            if (n_col < w.N) {
+            uint32_t c0 = h2_const_int(-(1024 + 8)), c1 = h2_const_int(-(64 + 8));
+            if (col_live) {
                 if (!w.is_gptq) {
                     cur_word = __ldg(w.q_scale + (size_t)grp * (w.N >> 3) + (n_col >> 3));
                     cur_h = __ldg(w.q_scale_max + grp);
                 } else {
-                    cur_word = __ldg(w.qzeros + (size_t)grp * (w.N >> 3) + (n_col >> 3));
                     cur_h = __ldg(w.gptq_scales + (size_t)grp * w.N + n_col);
+                    const int z1 = (int)((zw_next >> ((n_col & 7) * 4)) & 15u) + 1;
+                    const uint16_t h0 = __half_as_ushort(__int2half_rn(-(1024 + z1))), h1 = __half_as_ushort(__int2half_rn(-(64 + z1)));
+                    c0 = (uint32_t)h0 * 0x00010001u;
+                    c1 = (uint32_t)h1 * 0x00010001u;
+                    if (c_ks + ns < my1) zw_next = __ldg(w.qzeros + (size_t)(grp + 1) * (w.N >> 3) + (n_col >> 3));   // GPTQ: one region
                 }
             }
 
-            // (b) previous group of this WG: MMAs done -> D readable, A buffer free
-            if (pending) drain();
-            TC_GSTAMP(1);
-
-            // (c) unpack my block's slabs of this group into TMEM
-            mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
-            phases ^= 1u << cstage;
-            TC_GSTAMP(2);
+            // (b) my block's slabs of this group have landed
+            mbar_wait(wbar + 8 * cstage, (wphase >> cstage) & 1u);
+            wphase ^= 1u << cstage;
             const uint8_t* sp = ring_p + cstage * stage_bytes;
-            const uint32_t a_dst = t_a + lane_sel;
-            switch (bits) {
-                case 4:
-                    if (w.is_gptq) tc_dequant_group<4, 2>(sp, ns, lane, a_dst);
-                    else tc_dequant_group<4, 1>(sp, ns, lane, a_dst);
-                    break;
-                case 5: tc_dequant_group<5, 0>(sp, ns, lane, a_dst); break;
-                case 3: tc_dequant_group<3, 0>(sp, ns, lane, a_dst); break;
-                case 6: tc_dequant_group<6, 0>(sp, ns, lane, a_dst); break;
-                case 2: tc_dequant_group<2, 0>(sp, ns, lane, a_dst); break;
-                default: tc_dequant_group<8, 0>(sp, ns, lane, a_dst); break;
-            }
-            TC_GSTAMP(3);
-            tmem_wait_st();
-
-            // everything above depended only on the weights; from here on we need the previous kernel's output
-            if (!waited) {
-                griddep_wait();
-                waited = true;
-                after_wait();
-                TC_STAMP(2);
-            }
-            if (!act_issued) {           // the segment's activations (UMMA layout, written by tc_prep_kernel): one bulk copy
-                act_issued = true;
-                if (warp == 0 && elect_one()) {
-                    const uint32_t bytes = (uint32_t)(ks1 - ks0) * SLAB_K * 16;
-                    mbar_arrive_expect_tx(bar_act, bytes);
-                    bulk_copy_g2s(act_a, reinterpret_cast<const uint8_t*>(mt.xp) + (size_t)ks0 * SLAB_K * 16, bytes, bar_act);
+            const int nchunks = (ns + 1) >> 1;
+#pragma unroll 1
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int nsl = min(2, ns - 2 * ch);
+                if (a_uses >= 3u) {              // the MMAs that read this A buffer three chunks ago have retired
+                    mbar_wait(barA + 8 * ab, (phaseA >> ab) & 1u);
+                    phaseA ^= 1u << ab;
+                    tc_fence_after();
                 }
-                mbar_wait(bar_act, act_phase);
-                TC_STAMP(3);
-            }
-            tc_fence_before();
-            bar_sync(1 + wg, 128);
-            TC_GSTAMP(4);
-
-            // (d) one elected lane of the WG's first warp feeds the tensor core: 2 MMAs (K = 16) per slab
-            if (wq == 0) {
-                tc_fence_after();
-                const uint64_t bd0 = make_b_desc(act_a + (uint32_t)((gk - ks0) * SLAB_K / 8) * 128);
-                const uint32_t t_c = mode == 1 ? t_offs : t_ones;
-                if (elect_one()) {
-                    // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
-                    if (ns == 4) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            umma_ts(t_d, t_a + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
-                            if (mode) umma_ts(t_d2, t_c, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
-                        }
-                    } else {
-                        for (int j = 0; j < 2 * ns; ++j) {
-                            umma_ts(t_d, t_a + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
-                            if (mode) umma_ts(t_d2, t_c, bd0 + (uint64_t)(j * 16), TC_IDESC, j > 0 ? 1u : 0u);
+                const uint32_t a_dst = t_a + ab * 32 + lane_sel;
+                switch (bits) {
+                    case 4: tc_dequant_chunk<4>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                    case 5: tc_dequant_chunk<5>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                    case 3: tc_dequant_chunk<3>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                    case 6: tc_dequant_chunk<6>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                    case 2: tc_dequant_chunk<2>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                    default: tc_dequant_chunk<8>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
+                }
+                tmem_wait_st();
+                // everything above depended only on the weights; from here on we need the previous kernel's output
+                if (!waited) {
+                    griddep_wait();
+                    waited = true;
+                    after_wait();
+                    TC_STAMP(2);
+                }
+                if (!act_started) {              // first chunk of the segment: the activations of the groups primed above
+                    act_started = true;
+                    if (wq == 0) {
+                        int t_ks = my0, t_r = c_r, t_spg = c_spg, t_end = c_end;
+                        for (int st = 0; st < primed; ++st) {
+                            const int tn = min(t_spg, t_end - t_ks);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(abar + 8 * st, (uint32_t)tn * SLAB_K * 16);
+                                bulk_copy_g2s(act_ring + st * TC_ACT_STAGE, asrc + (size_t)t_ks * SLAB_K * 16, (uint32_t)tn * SLAB_K * 16, abar + 8 * st);
+                            }
+                            t_ks += tn;
+                            if (t_ks >= t_end && t_r + 1 < nreg) {
+                                ++t_r;
+                                t_spg = 1 << w.reg[t_r].spg_log2;
+                                t_end = tc_region_end(w, t_r);
+                            }
                         }
                     }
-                    umma_commit(bar_mma);
                 }
-                __syncwarp();
+                tc_fence_before();
+                bar_sync(1 + wg, 128);
+                if (wq == 0) {                   // the WG's first warp feeds the tensor core: 2 MMAs (K = 16) per slab
+                    tc_fence_after();
+                    if (ch == 0) {
+                        mbar_wait(abar + 8 * cstage, (aphase >> cstage) & 1u);
+                        aphase ^= 1u << cstage;
+                    }
+                    // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
+                    const uint64_t bd0 = make_b_desc(act_ring + cstage * TC_ACT_STAGE + (uint32_t)ch * 1024u);
+                    const uint32_t td = t_d + dsel * 16, ta = t_a + ab * 32;
+                    if (elect_one()) {
+                        if (nsl == 2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
+                        }
+                        umma_commit(barA + 8 * ab);
+                        if (ch == nchunks - 1) umma_commit(barD + 8 * dsel);
+                    }
+                    __syncwarp();
+                }
+                ab = (ab == 2u) ? 0u : ab + 1u;
+                ++a_uses;
             }
-            TC_GSTAMP(5);
-            ++gi_dbg;
+            // (c) read back the PREVIOUS group while this one's MMAs run (and re-arm its stage), then step the cursor
+            if (pending) drain();
             pending = true;
+            pend_d = dsel;
+            dsel ^= 1u;
             pend_word = cur_word;
             pend_h = cur_h;
-            pend_mode = mode;
-
-            // (e) refill my weight stage, advance to this WG's next group
-            cstage = (cstage + 1 == TC_STAGES) ? 0 : cstage + 1;
-            if (fetch_ks < ks1) issue();
-            int nk = gk + ns;
-            if (nk < ks1) nk += group_len(nk);
-            gk = nk;
+            cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
+            c_ks += ns;
+            ++c_grp;
+            if (c_ks >= c_end && c_r + 1 < nreg) {
+                ++c_r;
+                c_bits = w.reg[c_r].bits;
+                c_spg = 1 << w.reg[c_r].spg_log2;
+                c_end = tc_region_end(w, c_r);
+                c_grp = w.reg[c_r].group_base;
+            }
         }
         if (pending) drain();
-        if (ks0 < ks1) act_phase ^= 1u;      // this activation barrier completed one phase (uniform across threads)
         if (!waited) {                   // a CTA whose snapped range is empty still takes part in the fix-up below
             griddep_wait();
             waited = true;
@@ -803,13 +828,18 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
         for (int r = 0; r < mats[i].w.num_regions; ++r)
             stage_bytes = std::max(stage_bytes, (1 << mats[i].w.reg[r].spg_log2) * block_bytes(mats[i].w.reg[r].bits));
     EXL2B_REQUIRE(stage_bytes > 0 && stage_bytes <= 4096, "quantisation groups above 128 rows are not supported by the tcgen05 kernel");
-    const long long seg_max = std::min((long long)P.KS, (units + grid - 1) / grid + 4);      // + group snapping slack
     P.tc_stage_bytes = stage_bytes;
-    P.tc_act_bytes = (int)(seg_max * SLAB_K * 16);                                           // 16 B per k (8 token slots)
     const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + GEMV_MTOK * 128 * 2 + 128 + 1023) / 1024) * 1024;
     P.tc_act_off = header;
-    const size_t smem_total = (size_t)header + P.tc_act_bytes + (size_t)TC_WARPS * TC_STAGES * stage_bytes;
-    EXL2B_REQUIRE(smem_total <= 200 * 1024, "K range per CTA too large for shared memory (%zu bytes)", smem_total);
+    // as many stages (<= 4) as leave room for the intended number of CTAs per SM (227 KB of shared memory, 1 KB reserved per CTA)
+    const size_t smem_budget = (size_t)(227 * 1024) / (size_t)std::max(1, g_tc_ctas_per_sm) - 1024;
+    int stages = TC_MAX_STAGES;
+    auto smem_for = [&](int st) { return (size_t)header + (size_t)st * (2 * TC_ACT_STAGE + (size_t)TC_WARPS * stage_bytes); };
+    while (stages > 2 && smem_for(stages) > smem_budget) --stages;
+    P.tc_stages = stages;
+    P.tc_act_bytes = 2 * stages * TC_ACT_STAGE;
+    const size_t smem_total = smem_for(stages);
+    EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes)", smem_total);
     EXL2B_REQUIRE((size_t)mats[0].w.K * 16 <= TC_XP_BYTES_PER_MAT, "K too large for the activation scratch");
     extern unsigned long long* g_dbg;
     extern int g_dbg_cta, g_dbg_slot;

@@ -73,7 +73,8 @@ struct GemvParams {
     int dbg_cta;
     int tc_stage_bytes;    // tcgen05 kernel: bytes of one weight stage (largest group of one 32-column block)
     int tc_act_off;        // tcgen05 kernel: shared-memory offset of the staged activations
-    int tc_act_bytes;      // tcgen05 kernel: capacity of the staged activations (16 B per k)
+    int tc_act_bytes;      // tcgen05 kernel: bytes of the two activation rings
+    int tc_stages;         // tcgen05 kernel: pipeline stages (groups in flight per warp), 2..4
     int row0;              // first token row of this pass (RoPE position bookkeeping)
     GemvExtras ex;
 };
