@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        extra = os.environ.get("EXL2B_NVCC_EXTRA", "").split()        # e.g. -DEXL2B_TC_PROFILE for tools/microbench.py --phases
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

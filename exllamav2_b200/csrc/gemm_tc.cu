@@ -25,18 +25,19 @@
 //     silu(gate)*up epilogues are the ones of the mma.sync kernel (fixed-order, deterministic).
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include "dequant.cuh"
 #include "gemv.cuh"
 
 namespace exl2b {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 320;                   // 8 unpack warps (2 warpgroups) + 2 MMA-issue warps (one per warpgroup)
 constexpr int TC_WARPS = 8;
 constexpr int TC_MAX_STAGES = 4;                  // stage = one group (<= 4 slabs) of one 32-column block; count + size set per launch
 constexpr int TC_NTOK = 16;                       // UMMA N; tokens 8..15 alias tokens 0..7 (SBO = 0), only 8 are real
 constexpr int TC_ACT_STAGE = 2048;                // activations of one group: 128 k x 16 B (8 token slots)
-constexpr int TC_NBARS = TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 2 * 3 + 2 * 2;   // weights | act | A free | D ready
+constexpr int TC_NBARS = TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 2 * 3 + 2 * 2 + 2 * 3;   // weights | act | A free | D ready | A full
 constexpr int TC_SMEM_BARS = TC_NBARS * 8;
 constexpr int TC_SMEM_MISC = 128;                 // tmem base, rstd[8], flag
 constexpr int TC_TMEM_COLS = 256;
@@ -57,6 +58,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -163,6 +165,20 @@ __device__ __forceinline__ unsigned long long tc_gtimer() {
 }
 #define TC_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && tid == 0) P.dbg[i] = tc_gtimer(); if ((i) == 0 && tid == 0) atomicMin(P.dbg + 6, tc_gtimer()); } } while (0)
 
+// -DEXL2B_TC_PROFILE: accumulate clock64 deltas of the main loop's phases in a few warps of CTA dbg_cta (tools/microbench.py --phases)
+#ifdef EXL2B_TC_PROFILE
+#define TCP_DECL long long tcp_t = 0, tcp_acc[4] = {0, 0, 0, 0}; const bool tcp_on = P.dbg && blockIdx.x == P.dbg_cta;
+#define TCP_BEGIN do { if (tcp_on) tcp_t = clock64(); } while (0)
+#define TCP_END(i) do { if (tcp_on) { const long long tcp_n = clock64(); tcp_acc[i] += tcp_n - tcp_t; tcp_t = tcp_n; } } while (0)
+#define TCP_FLUSH do { if (tcp_on && lane == 0) { const int tcp_slot = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 8 ? 3 : -1; \
+    if (tcp_slot >= 0) for (int i = 0; i < 4; ++i) P.dbg[8 + tcp_slot * 4 + i] = (unsigned long long)tcp_acc[i]; } } while (0)
+#else
+#define TCP_DECL
+#define TCP_BEGIN do {} while (0)
+#define TCP_END(i) do {} while (0)
+#define TCP_FLUSH do {} while (0)
+#endif
+
 template <int BITS>
 __device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uint32_t* mw, uint32_t* ew) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
@@ -184,34 +200,36 @@ __device__ __forceinline__ void tc_load_words(const uint8_t* base, int lane, uin
     }
 }
 
-// 4-bit fields, exact: two-offset extraction (4 LOP3 + 1 SHF per 8 weights on the ALU pipe) and the offset + zero point
-// removed by one HADD2 per pair on the otherwise idle FMA pipe.  c0 = -(1024 + zero), c1 = -(64 + zero) as half2 bits;
-// EXL2: zero = 8 (qdq_4.cuh:34-60), GPTQ: zero = z + 1 per (group, column) (q_gemm_kernel_gptq.cuh:167-172).
-__device__ __forceinline__ void tc_dequant4(const uint32_t* mw, uint32_t c0, uint32_t c1, uint32_t* A) {
+// 4-bit fields in "two-offset form": value = offset + q with offset 1024 (even pair slots) or 64 (odd pair slots), i.e. the
+// bare (w & mask) | magic -- 4 LOP3 + 1 SHF per 8 weights and nothing else.  The offsets and the zero point are removed per
+// group AFTER the tensor core:  sum_k a_k (q_k - z) = D - (S1 + z * S0),  S1 = sum_k a_k * offset_k,  S0 = sum_k a_k;  S1 and
+// S0 do not depend on the output column, the MMA-issue warp computes them once per group from the staged activations.
+// Products (offset + q) * a are exact in the tensor core and fp32 accumulation sees operands < 2^11 |a|.
+__device__ __forceinline__ void tc_dequant4(const uint32_t* mw, uint32_t* A) {
     const uint32_t m0 = 0x000f000fu, g0 = 0x64006400u, m1 = 0x00f000f0u, g1 = 0x54005400u;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         const uint32_t x = mw[w], y = x >> 8;
-        A[w * 4 + 0] = h2add_bits(and_or(x, m0, g0), c0);
-        A[w * 4 + 1] = h2add_bits(and_or(x, m1, g1), c1);
-        A[w * 4 + 2] = h2add_bits(and_or(y, m0, g0), c0);
-        A[w * 4 + 3] = h2add_bits(and_or(y, m1, g1), c1);
+        A[w * 4 + 0] = and_or(x, m0, g0);
+        A[w * 4 + 1] = and_or(x, m1, g1);
+        A[w * 4 + 2] = and_or(y, m0, g0);
+        A[w * 4 + 3] = and_or(y, m1, g1);
     }
 }
 // unpack slab i of this warp's block stage (contiguous at sp) into 16 TMEM columns at a_taddr
 template <int BITS>
-__device__ __forceinline__ void tc_dequant_slab(const uint8_t* sp, int i, int lane, uint32_t a_taddr, uint32_t c0, uint32_t c1) {
+__device__ __forceinline__ void tc_dequant_slab(const uint8_t* sp, int i, int lane, uint32_t a_taddr) {
     uint32_t mw[8], ew[2], A[16];
     tc_load_words<BITS>(sp + i * block_bytes(BITS), lane, mw, ew);
-    if constexpr (BITS == 4) tc_dequant4(mw, c0, c1, A);
+    if constexpr (BITS == 4) tc_dequant4(mw, A);
     else dequant_block_exl2<BITS>(mw, ew, A);
     tmem_st16(a_taddr, A);
 }
 // one chunk = slabs [s0, s0 + nsl) of the stage, nsl <= 2, into one A buffer
 template <int BITS>
-__device__ __forceinline__ void tc_dequant_chunk(const uint8_t* sp, int s0, int nsl, int lane, uint32_t a_taddr, uint32_t c0, uint32_t c1) {
-    tc_dequant_slab<BITS>(sp, s0, lane, a_taddr, c0, c1);
-    if (nsl == 2) tc_dequant_slab<BITS>(sp, s0 + 1, lane, a_taddr + 16, c0, c1);
+__device__ __forceinline__ void tc_dequant_chunk(const uint8_t* sp, int s0, int nsl, int lane, uint32_t a_taddr) {
+    tc_dequant_slab<BITS>(sp, s0, lane, a_taddr);
+    if (nsl == 2) tc_dequant_slab<BITS>(sp, s0 + 1, lane, a_taddr + 16);
 }
 
 // ---- activation prep: RMSNorm + q_perm gather + UMMA core-matrix layout, once per launch ------------------------------
@@ -278,7 +296,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);         // provably warp-uniform (UMMA operands live in uniform registers)
-    const int wg = warp >> 2, wq = warp & 3, tidw = tid & 127;       // warpgroup, TMEM lane quadrant, thread = weight column
+    const bool is_mma = warp >= TC_WARPS;                           // warps 8, 9: tensor-core issue for warpgroup 0, 1
+    const int wg = is_mma ? warp - TC_WARPS : warp >> 2;            // the warpgroup this warp belongs to / serves
+    const int rwg = is_mma ? 2 : wg;                                // role in the epilogue (issue warps take no part)
+    const int wq = warp & 3, tidw = tid & 127;                      // TMEM lane quadrant, thread = weight column
 
     griddep_launch_dependents();
     TC_STAMP(0);
@@ -290,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const uint32_t abar = smem0 + (TC_WARPS * TC_MAX_STAGES + wg * TC_MAX_STAGES) * 8;          // my WG's activation stages
     const uint32_t barA = smem0 + (TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + wg * 3) * 8;  // A buffer free (its MMAs retired)
     const uint32_t barD = smem0 + (TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 6 + wg * 2) * 8;   // accumulator complete
+    const uint32_t barF = smem0 + (TC_WARPS * TC_MAX_STAGES + 2 * TC_MAX_STAGES + 10 + wg * 3) * 8;  // A buffer full (4 warps arrive)
     uint8_t* misc = smem + TC_SMEM_BARS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
     int* flag_s = reinterpret_cast<int*>(misc + 64);
@@ -297,6 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     float* comb_s = reinterpret_cast<float*>(misc + TC_SMEM_MISC);  // [8][128] WG1 totals
     half* tile_s = reinterpret_cast<half*>(comb_s + GEMV_MTOK * 128);   // [8][128] fp16 outputs (RoPE partner exchange)
     float* ssq_s = reinterpret_cast<float*>(tile_s + GEMV_MTOK * 128);  // [4][8] per-warp sums of squares
+    float* corr_s = ssq_s + 32 + wg * (TC_MAX_STAGES * 16);             // [stage][S1[8] | S0[8]] of my warpgroup's 4-bit groups
     const uint32_t act_ring = smem0 + P.tc_act_off + wg * NS * TC_ACT_STAGE;
     const int ring_off = P.tc_act_off + 2 * NS * TC_ACT_STAGE;
     uint8_t* ring_p = smem + ring_off + warp * NS * stage_bytes;
@@ -304,29 +327,32 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const int M = P.M, KS = P.KS;
 
     // ---- one-time setup: barriers, TMEM ----
-    if (lane == 0) {
+    if (lane == 0 && !is_mma) {
         for (int st = 0; st < NS; ++st) mbar_init(wbar + 8 * st, 1);
         if (wq == 0) {
             for (int st = 0; st < NS; ++st) mbar_init(abar + 8 * st, 1);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) mbar_init(barA + 8 * i, 1);
-            mbar_init(barD, 1);
-            mbar_init(barD + 8, 1);
+            for (int i = 0; i < 3; ++i) {
+                mbar_init(barA + 8 * i, 1);
+                mbar_init(barF + 8 * i, 4);
+            }
+            mbar_init(barD, 2);            // tcgen05.commit of the group's last chunk + the issue warp's own arrive (S1 / S0 written)
+            mbar_init(barD + 8, 2);
         }
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    __syncwarp();
+    // (a warp's weight barriers are used by that warp alone: it may start fetching right away; the tensor-memory allocation
+    //  and the CTA-wide barrier that publishes the shared barriers come after the first requests are in flight)
+    bool setup_done = false;
+    uint32_t tmem_base = 0, t_a = 0, t_d = 0;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const uint32_t t_a = tmem_base + wg * TC_COLS_PER_WG, t_d = t_a + TC_A_BUFS * 32;   // A: 3 x 32 columns, D: 2 x 16
 
     const unsigned U = (unsigned)P.total_units, G = gridDim.x;
     const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
 
-    uint32_t wphase = 0, aphase = 0, phaseA = 0, phaseD = 0;     // parity bits per barrier
+    uint32_t wphase = 0, aphase = 0, phaseA = 0, phaseD = 0, phaseF = 0;     // parity bits per barrier
+    TCP_DECL
     uint32_t ab = 0, a_uses = 0, dsel = 0;                        // A buffer / accumulator rotation of this WG (across segments)
     bool waited = false;
     auto after_wait = [&]() {       // first point where the previous kernel's output may be read
@@ -358,6 +384,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
         const uint8_t* asrc = reinterpret_cast<const uint8_t*>(mt.xp);
         const int nreg = w.num_regions;
+        // per-matrix fields used in the loops below, pinned in registers (indexed kernel-parameter reads are slow and the
+        // compiler would otherwise re-read them every group)
+        const bool gptq = w.is_gptq != 0;
+        const uint32_t* sc_w = (gptq ? w.qzeros : w.q_scale) + (n_col >> 3);     // my column's nibble word of group 0
+        const half* sc_h = gptq ? w.gptq_scales + n_col : w.q_scale_max;
+        int n8 = w.N >> 3;
+        asm volatile("" : "+l"(sc_w));
+        asm volatile("" : "+l"(sc_h));
+        asm volatile("" : "+r"(n8));
+        const int nib_sh = (n_col & 7) * 4;
 
         // Group cursors: position + the current region's parameters in registers, so that stepping to the next group
         // is a handful of integer ops; the kernel-parameter region table is only read when a region boundary is crossed.
@@ -399,129 +435,69 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         // griddepcontrol.wait, requested by re-walking the same groups with a scratch copy of the cursor
         int primed = 0;
 #pragma unroll 1
-        for (; primed < NS && f_ks < my1; ++primed) issue(true, false);
+        for (; !is_mma && primed < NS && f_ks < my1; ++primed) issue(true, false);
+        if (!setup_done) {
+            setup_done = true;
+            if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            tmem_base = *tmem_slot;
+            t_a = tmem_base + wg * TC_COLS_PER_WG;          // A: 3 x 32 columns, D: 2 x 16
+            t_d = t_a + TC_A_BUFS * 32;
+        }
         TC_STAMP(1);
 
-        // ---- the WG pipeline.  Per chunk (<= 2 slabs = 64 k): unpack -> tcgen05.st into a free A buffer -> WG barrier ->
-        //      one lane issues the chunk's MMAs and commits to "A buffer free"; the group's last chunk also commits to
-        //      "accumulator complete".  The accumulator of group g is read back (tcgen05.ld, scaled, added) only after
-        //      group g+1's MMAs have been issued, so the tensor core and the unpack overlap.
-        float tot[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) tot[m] = 0.f;
-        bool pending = false, act_started = false;
-        uint32_t pend_d = 0;             // accumulator index of the pending (issued, not yet read back) group
-        uint32_t pend_word = 0;          // raw q_scale word / GPTQ scale of the pending group (decoded only when drained:
-        half pend_h = __float2half(0.f); //   the SM issues in order, so touching a load result early stalls the warp)
-        uint32_t zw_next = 0;            // GPTQ: qzeros word of the NEXT group (needed at unpack time, so fetched a group ahead)
-        if (w.is_gptq && col_live && c_ks < my1) zw_next = __ldg(w.qzeros + (size_t)c_grp * (w.N >> 3) + (n_col >> 3));
-
-        auto drain = [&]() {       // accumulator of the previous group -> running totals; its stage gets the next request
-            const uint32_t d = pend_d;
-            mbar_wait(barD + 8 * d, (phaseD >> d) & 1u);
-            phaseD ^= 1u << d;
-            tc_fence_after();
-            float pend_scale = 0.f;
-            if (col_live) {
-                if (!w.is_gptq) {
-                    const int nib = (int)((pend_word >> ((n_col & 7) * 4)) & 15u);
-                    pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), pend_h));    // qdq_util.cuh:24-30
-                } else {
-                    pend_scale = __half2float(pend_h);
-                }
-            }
-            float dd[MT];
-            if constexpr (MT == 1) tmem_ld1(t_d + d * 16 + lane_sel, dd[0]);
-            else tmem_ld8(t_d + d * 16 + lane_sel, dd);
-            tmem_wait_ld();
-#pragma unroll
-            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m], tot[m]);
-            tc_fence_before();
-            if (f_ks < my1) issue(true, true);       // the drained group's MMAs have retired: both of its stages are free
-        };
-
-        while (c_ks < my1) {
-            const int bits = c_bits;
-            const int ns = min(c_spg, c_end - c_ks);
-            const int grp = c_grp;
-
-            // (a) this group's scale for my column: requested now, decoded when the group is drained
-            uint32_t cur_word = 0;
-            half cur_h = __float2half(0.f);
-            uint32_t c0 = h2_const_int(-(1024 + 8)), c1 = h2_const_int(-(64 + 8));
-            if (col_live) {
-                if (!w.is_gptq) {
-                    cur_word = __ldg(w.q_scale + (size_t)grp * (w.N >> 3) + (n_col >> 3));
-                    cur_h = __ldg(w.q_scale_max + grp);
-                } else {
-                    cur_h = __ldg(w.gptq_scales + (size_t)grp * w.N + n_col);
-                    const int z1 = (int)((zw_next >> ((n_col & 7) * 4)) & 15u) + 1;
-                    const uint16_t h0 = __half_as_ushort(__int2half_rn(-(1024 + z1))), h1 = __half_as_ushort(__int2half_rn(-(64 + z1)));
-                    c0 = (uint32_t)h0 * 0x00010001u;
-                    c1 = (uint32_t)h1 * 0x00010001u;
-                    if (c_ks + ns < my1) zw_next = __ldg(w.qzeros + (size_t)(grp + 1) * (w.N >> 3) + (n_col >> 3));   // GPTQ: one region
-                }
-            }
-
-            // (b) my block's slabs of this group have landed
-            mbar_wait(wbar + 8 * cstage, (wphase >> cstage) & 1u);
-            wphase ^= 1u << cstage;
-            const uint8_t* sp = ring_p + cstage * stage_bytes;
-            const int nchunks = (ns + 1) >> 1;
+        if (is_mma) {
+            // ---- tensor-core issue warp of warpgroup wg: for every chunk wait until the four unpack warps have filled the
+            //      A buffer, issue its MMAs (2 per slab, K = 16), commit to "A buffer free" (+ "accumulator complete" at the
+            //      group's last chunk).  It never blocks the unpack warps: they only meet it through mbarriers.
+            int m_ks = my0, m_r = c_r, m_spg = c_spg, m_end = c_end, m_bits = c_bits, mstage = 0;
+            while (m_ks < my1) {
+                const int ns = min(m_spg, m_end - m_ks);
+                const int nchunks = (ns + 1) >> 1;
+                TCP_BEGIN;
+                mbar_wait(abar + 8 * mstage, (aphase >> mstage) & 1u);       // the group's activations have landed
+                aphase ^= 1u << mstage;
+                TCP_END(0);
+                const uint8_t* actp = smem + P.tc_act_off + (wg * NS + mstage) * TC_ACT_STAGE;
 #pragma unroll 1
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int nsl = min(2, ns - 2 * ch);
-                if (a_uses >= 3u) {              // the MMAs that read this A buffer three chunks ago have retired
-                    mbar_wait(barA + 8 * ab, (phaseA >> ab) & 1u);
-                    phaseA ^= 1u << ab;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int nsl = min(2, ns - 2 * ch);
+                    TCP_BEGIN;
+                    mbar_wait(barF + 8 * ab, (phaseF >> ab) & 1u);
+                    phaseF ^= 1u << ab;
                     tc_fence_after();
-                }
-                const uint32_t a_dst = t_a + ab * 32 + lane_sel;
-                switch (bits) {
-                    case 4: tc_dequant_chunk<4>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                    case 5: tc_dequant_chunk<5>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                    case 3: tc_dequant_chunk<3>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                    case 6: tc_dequant_chunk<6>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                    case 2: tc_dequant_chunk<2>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                    default: tc_dequant_chunk<8>(sp, 2 * ch, nsl, lane, a_dst, c0, c1); break;
-                }
-                tmem_wait_st();
-                // everything above depended only on the weights; from here on we need the previous kernel's output
-                if (!waited) {
-                    griddep_wait();
-                    waited = true;
-                    after_wait();
-                    TC_STAMP(2);
-                }
-                if (!act_started) {              // first chunk of the segment: the activations of the groups primed above
-                    act_started = true;
-                    if (wq == 0) {
-                        int t_ks = my0, t_r = c_r, t_spg = c_spg, t_end = c_end;
-                        for (int st = 0; st < primed; ++st) {
-                            const int tn = min(t_spg, t_end - t_ks);
-                            if (elect_one()) {
-                                mbar_arrive_expect_tx(abar + 8 * st, (uint32_t)tn * SLAB_K * 16);
-                                bulk_copy_g2s(act_ring + st * TC_ACT_STAGE, asrc + (size_t)t_ks * SLAB_K * 16, (uint32_t)tn * SLAB_K * 16, abar + 8 * st);
+                    TCP_END(0);
+                    if (ch == 0) {
+                        // (all four unpack warps are past the read-back of the group that last used this stage's S1 / S0)
+                        if (m_bits == 4) {
+                            // lane = (token t, k-quarter kq): sums over the 8-k core-matrix rows 4*kq .. 4*kq+3 of every slab
+                            const int t = lane & 7, kq = lane >> 3;
+                            float s1 = 0.f, s0 = 0.f;
+                            for (int row = kq; row < ns * 4; row += 4) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(actp + row * 128 + t * 16);
+                                const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const half2*>(&v.y));
+                                const float2 f2 = __half22float2(*reinterpret_cast<const half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const half2*>(&v.w));
+                                const float e = (f0.x + f0.y) + (f2.x + f2.y), o = (f1.x + f1.y) + (f3.x + f3.y);   // even / odd pair slots
+                                s1 = fmaf(1024.f, e, fmaf(64.f, o, s1));
+                                s0 += e + o;
                             }
-                            t_ks += tn;
-                            if (t_ks >= t_end && t_r + 1 < nreg) {
-                                ++t_r;
-                                t_spg = 1 << w.reg[t_r].spg_log2;
-                                t_end = tc_region_end(w, t_r);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                            if (lane < 8) {
+                                corr_s[mstage * 16 + lane] = s1;
+                                corr_s[mstage * 16 + 8 + lane] = s0;
                             }
                         }
+                        __syncwarp();
+                        if (elect_one()) mbar_arrive(barD + 8 * dsel);
                     }
-                }
-                tc_fence_before();
-                bar_sync(1 + wg, 128);
-                if (wq == 0) {                   // the WG's first warp feeds the tensor core: 2 MMAs (K = 16) per slab
-                    tc_fence_after();
-                    if (ch == 0) {
-                        mbar_wait(abar + 8 * cstage, (aphase >> cstage) & 1u);
-                        aphase ^= 1u << cstage;
-                    }
+                    TCP_END(1);
                     // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
-                    const uint64_t bd0 = make_b_desc(act_ring + cstage * TC_ACT_STAGE + (uint32_t)ch * 1024u);
+                    const uint64_t bd0 = make_b_desc(act_ring + mstage * TC_ACT_STAGE + (uint32_t)ch * 1024u);
                     const uint32_t td = t_d + dsel * 16, ta = t_a + ab * 32;
                     if (elect_one()) {
                         if (nsl == 2) {
@@ -531,21 +507,175 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 #pragma unroll
                             for (int j = 0; j < 2; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
                         }
+#ifdef EXL2B_TC_PROFILE
+                    }
+                    __syncwarp();
+                    TCP_END(2);
+                    if (elect_one()) {
+#endif
                         umma_commit(barA + 8 * ab);
                         if (ch == nchunks - 1) umma_commit(barD + 8 * dsel);
                     }
                     __syncwarp();
+                    TCP_END(3);
+                    ab = (ab == 2u) ? 0u : ab + 1u;
                 }
-                ab = (ab == 2u) ? 0u : ab + 1u;
-                ++a_uses;
+                dsel ^= 1u;
+                mstage = (mstage + 1 == NS) ? 0 : mstage + 1;
+                m_ks += ns;
+                if (m_ks >= m_end && m_r + 1 < nreg) {
+                    ++m_r;
+                    m_spg = 1 << w.reg[m_r].spg_log2;
+                    m_end = tc_region_end(w, m_r);
+                    m_bits = w.reg[m_r].bits;
+                }
+            }
+        }
+
+
+        // everything above depended only on the weights; from here on the previous kernel's output is needed
+        if (!waited && !is_mma) {
+            griddep_wait();
+            waited = true;
+            after_wait();
+            TC_STAMP(2);
+        }
+        if (!is_mma && wq == 0) {            // the activations of the groups primed above (same walk, scratch cursor)
+            int t_ks = my0, t_r = c_r, t_spg = c_spg, t_end = c_end;
+            for (int st = 0; st < primed; ++st) {
+                const int tn = min(t_spg, t_end - t_ks);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(abar + 8 * st, (uint32_t)tn * SLAB_K * 16);
+                    bulk_copy_g2s(act_ring + st * TC_ACT_STAGE, asrc + (size_t)t_ks * SLAB_K * 16, (uint32_t)tn * SLAB_K * 16, abar + 8 * st);
+                }
+                t_ks += tn;
+                if (t_ks >= t_end && t_r + 1 < nreg) {
+                    ++t_r;
+                    t_spg = 1 << w.reg[t_r].spg_log2;
+                    t_end = tc_region_end(w, t_r);
+                }
+            }
+        }
+
+        // ---- the unpack pipeline of a warp.  Per chunk (<= 2 slabs = 64 k): wait for a free A buffer -> unpack ->
+        //      tcgen05.st -> arrive on "A full"; the issue warp does the rest.  The accumulator of group g is read back
+        //      (tcgen05.ld, scaled, added) only after group g+1 has been unpacked, so tensor core and unpack overlap.
+        float tot[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tot[m] = 0.f;
+        bool pending = false;
+        // State of a group between its unpack and its read-back.  Two instances used alternately (the loop below is unrolled
+        // by two): a scale loaded at the top of group g is first touched when g is read back, at the END of group g+1 -- no
+        // register move in between that would make the in-order warp wait for the load.
+        struct GroupState {
+            uint32_t word;       // raw q_scale word (EXL2)
+            half h;              // q_scale_max[group] (EXL2) / scale of (group, column) (GPTQ)
+            int z;               // zero point when unpacked in two-offset form (EXL2: 8, GPTQ: z + 1), -1: exact unpack
+            uint32_t d;          // accumulator index
+            int stage;           // pipeline stage (where the issue warp left S1 / S0)
+        };
+        GroupState ga = {0u, __float2half(0.f), -1, 0u, 0}, gb = ga;
+        uint32_t zw_next = 0;            // GPTQ: qzeros word of the NEXT group, fetched a group ahead
+        if (!is_mma && gptq && col_live && c_ks < my1) zw_next = __ldg(sc_w + (size_t)c_grp * n8);
+
+        auto drain = [&](const GroupState& g) {       // accumulator of group g -> running totals; its stage gets the next request
+            const uint32_t d = g.d;
+            mbar_wait(barD + 8 * d, (phaseD >> d) & 1u);
+            phaseD ^= 1u << d;
+            tc_fence_after();
+            TCP_END(2);
+            float pend_scale = 0.f;
+            if (col_live) {
+                if (!gptq) {
+                    const int nib = (int)((g.word >> nib_sh) & 15u);
+                    pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), g.h));    // qdq_util.cuh:24-30
+                } else {
+                    pend_scale = __half2float(g.h);
+                }
+            }
+            float dd[MT];
+            if constexpr (MT == 1) tmem_ld1(t_d + d * 16 + lane_sel, dd[0]);
+            else tmem_ld8(t_d + d * 16 + lane_sel, dd);
+            if (g.z >= 0) {              // remove the unpack offsets and the zero point
+                const float zf = (float)g.z;
+                const float* cs = corr_s + g.stage * 16;
+                tmem_wait_ld();
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m] - fmaf(zf, cs[8 + m], cs[m]), tot[m]);
+            } else {
+                tmem_wait_ld();
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m], tot[m]);
+            }
+            tc_fence_before();
+            if (f_ks < my1) issue(true, true);       // the drained group's MMAs have retired: both of its stages are free
+        };
+
+        auto group_step = [&](GroupState& cur, const GroupState& prev) {
+            const int bits = c_bits;
+            const int ns = min(c_spg, c_end - c_ks);
+            const int grp = c_grp;
+
+            // (a) this group's scale for my column: requested now, decoded when the group is read back
+            cur.word = 0u;
+            cur.h = __float2half(0.f);
+            cur.z = bits == 4 ? 8 : -1;
+            if (col_live) {
+                if (!gptq) {
+                    cur.word = __ldg(sc_w + (size_t)grp * n8);
+                    cur.h = __ldg(sc_h + grp);
+                } else {
+                    cur.h = __ldg(sc_h + (size_t)grp * (n8 * 8));
+                    cur.z = (int)((zw_next >> nib_sh) & 15u) + 1;                                   // q_gemm_kernel_gptq.cuh:167-172
+                    if (c_ks + ns < my1) zw_next = __ldg(sc_w + (size_t)(grp + 1) * n8);           // GPTQ: one region
+                }
+            }
+            cur.d = dsel;
+            cur.stage = cstage;
+
+            // (b) my block's slabs of this group have landed
+            TCP_BEGIN;
+            mbar_wait(wbar + 8 * cstage, (wphase >> cstage) & 1u);
+            wphase ^= 1u << cstage;
+            TCP_END(0);
+            const uint8_t* sp = ring_p + cstage * stage_bytes;
+            const int nchunks = (ns + 1) >> 1;
+            auto run_chunks = [&](auto tag) {
+                constexpr int B = decltype(tag)::value;
+#pragma unroll 1
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int nsl = min(2, ns - 2 * ch);
+                    TCP_BEGIN;
+                    if (a_uses >= 3u) {              // the MMAs that read this A buffer three chunks ago have retired
+                        mbar_wait(barA + 8 * ab, (phaseA >> ab) & 1u);
+                        phaseA ^= 1u << ab;
+                        tc_fence_after();
+                    }
+                    TCP_END(0);
+                    tc_dequant_chunk<B>(sp, 2 * ch, nsl, lane, t_a + ab * 32 + lane_sel);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(barF + 8 * ab);     // 1 of 4: this warp's 32 rows of the A buffer are in place
+                    ab = (ab == 2u) ? 0u : ab + 1u;
+                    ++a_uses;
+                    TCP_END(1);
+                }
+            };
+            switch (bits) {
+                case 4: run_chunks(std::integral_constant<int, 4>{}); break;
+                case 5: run_chunks(std::integral_constant<int, 5>{}); break;
+                case 3: run_chunks(std::integral_constant<int, 3>{}); break;
+                case 6: run_chunks(std::integral_constant<int, 6>{}); break;
+                case 2: run_chunks(std::integral_constant<int, 2>{}); break;
+                default: run_chunks(std::integral_constant<int, 8>{}); break;
             }
             // (c) read back the PREVIOUS group while this one's MMAs run (and re-arm its stage), then step the cursor
-            if (pending) drain();
+            TCP_BEGIN;
+            if (pending) drain(prev);
+            TCP_END(3);
             pending = true;
-            pend_d = dsel;
             dsel ^= 1u;
-            pend_word = cur_word;
-            pend_h = cur_h;
             cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
             c_ks += ns;
             ++c_grp;
@@ -556,9 +686,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 c_end = tc_region_end(w, c_r);
                 c_grp = w.reg[c_r].group_base;
             }
+        };
+        bool last_a = false;
+        while (!is_mma && c_ks < my1) {
+            group_step(ga, gb);
+            last_a = true;
+            if (c_ks >= my1) break;
+            group_step(gb, ga);
+            last_a = false;
         }
-        if (pending) drain();
-        if (!waited) {                   // a CTA whose snapped range is empty still takes part in the fix-up below
+        if (pending) {
+            if (last_a) drain(ga);
+            else drain(gb);
+        }
+        if (!waited && !is_mma) {        // a CTA whose snapped range is empty still takes part in the fix-up below
             griddep_wait();
             waited = true;
             after_wait();
@@ -567,7 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
         // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
         __syncthreads();
-        if (wg == 1) {
+        if (rwg == 1) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) comb_s[m * 128 + tidw] = tot[m];
         }
@@ -579,7 +720,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
         const bool paired = P.epilogue != EPI_STORE;
         const bool has_rstd = P.ex.sumsq_in != nullptr;
-        if (wg == 0) {
+        if (rwg == 0) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) tot[m] += comb_s[m * 128 + tidw];
         }
@@ -592,12 +733,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             finisher = true;
         } else {
             float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * TC_RED_FLOATS;
-            if (wg == 0) {
+            if (rwg == 0) {
 #pragma unroll
                 for (int m = 0; m < MT; ++m) __stcg(wsp + m * 128 + tidw, tot[m]);
             }
-            __threadfence();
-            __syncthreads();
+            __syncthreads();             // every partial of this CTA is written (CTA-scope happens-before to thread 0)
             int expected = nc, cidx = gs;
             if (paired) {
                 const GemvMat& other = P.mat[1 - mi];
@@ -605,15 +745,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 expected += tc_cta_of_unit(ob + KS - 1, G, U) - tc_cta_of_unit(ob, G, U) + 1;
                 cidx = P.mat[0].strip_begin + strip;
             }
-            if (tid == 0) {
-                const unsigned int old = atomicAdd(P.counters + cidx, 1u);
+            if (tid == 0) {              // release our partials / acquire everybody else's: one acq_rel RMW at GPU scope
+                unsigned int old;
+                asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(P.counters + cidx), "r"(1u) : "memory");
                 *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
             }
             __syncthreads();
             if (*flag_s) {
                 finisher = true;
-                __threadfence();
-                if (wg == 0) {
+                if (rwg == 0) {
                     if (!paired) {
                         const float* base = P.ws + (size_t)gs * P.maxc * TC_RED_FLOATS;
 #pragma unroll
@@ -646,7 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
 
         // ---- the finishing CTA's first warpgroup turns the sums into outputs (thread = column) ----
-        if (finisher && wg == 0) {
+        if (finisher && rwg == 0) {
             const GemvMat& mo = paired ? P.mat[0] : mt;         // where the result goes
             const bool col_ok = n_col < mo.w.N;
             half hv[MT];
@@ -731,6 +871,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
         __syncthreads();
         TC_STAMP(5);
+        TCP_FLUSH;
         u += seg;
     }
 
@@ -829,7 +970,7 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
             stage_bytes = std::max(stage_bytes, (1 << mats[i].w.reg[r].spg_log2) * block_bytes(mats[i].w.reg[r].bits));
     EXL2B_REQUIRE(stage_bytes > 0 && stage_bytes <= 4096, "quantisation groups above 128 rows are not supported by the tcgen05 kernel");
     P.tc_stage_bytes = stage_bytes;
-    const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + GEMV_MTOK * 128 * 2 + 128 + 1023) / 1024) * 1024;
+    const int header = ((TC_SMEM_BARS + TC_SMEM_MISC + GEMV_MTOK * 128 * 4 + GEMV_MTOK * 128 * 2 + 128 + 2 * TC_MAX_STAGES * 64 + 1023) / 1024) * 1024;
     P.tc_act_off = header;
     // as many stages (<= 4) as leave room for the intended number of CTAs per SM (227 KB of shared memory, 1 KB reserved per CTA)
     const size_t smem_budget = (size_t)(227 * 1024) / (size_t)std::max(1, g_tc_ctas_per_sm) - 1024;

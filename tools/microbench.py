@@ -128,7 +128,7 @@ def main():
                         r = st[i]
                         print(json.dumps({"shape": name, "M": M, "cta": cta, "launch": i, "grid_start": r[6] - t0, "grid_end": r[7] - t0,
                                           "cta[start,prefetched,wait_done,staged,consumed,done]": [x - t0 for x in r[:6]],
-                                          "groups[top,drained,weights,dequant,synced,issued]x3": [(x - t0 if x else 0) for x in r[8:26]]}), flush=True)
+                                          "clk[w0|w1|w4: waits(weights+A_free),unpack,drain:wait_D,drain:rest ; w8(issue): waits(act+A_full),S+arrive,MMAs,commits]": [r[8:12], r[12:16], r[16:20], r[20:24]]}), flush=True)
             t_eager = time_loop(run_new, 5)
             # graph-captured cycle (no host launch overhead)
             g = torch.cuda.CUDAGraph()
