@@ -67,7 +67,7 @@ __device__ __forceinline__ half2 hadamard32_h(half2 w2, int lane) {      // bit-
 __device__ __forceinline__ float nib_f(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388616.0f; }
 
 template <int HD>
-__global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_constant__ AttnQ4Params P) {
+__global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_constant__ AttnQ4Params P) {
     constexpr int ROWB = HD / 2;            // packed bytes per (position, kv head)
     constexpr int NSC = HD / 32;            // scales per (position, kv head)
     constexpr int VEC = HD / 32;            // values per lane in the dims-on-lanes phase
@@ -87,13 +87,55 @@ __global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_consta
     float* sc = reinterpret_cast<float*>(pages_s + ((P.pages_per_seq + 3) & ~3));   // [max_ctx + q_len]
 
     griddep_launch_dependents();
-    griddep_wait();
+    // ---- 0. before the dependency wait: everything that only touches state written by EARLIER steps / layers -- the
+    //      sequence length, the page table and the cached rows (this layer's cache was last written one decode step ago; the
+    //      kernel in front of us in the stream, the Q|K|V projection, writes none of it).  The first cached K row of every
+    //      thread and the first 16 cached V rows of every warp are already in registers when q / k_new / v_new arrive.
     const int seqlen = P.cache_seqlens[b];
-    for (int i = tid; i < P.pages_per_seq; i += AQ_THREADS) pages_s[i] = P.block_table[(size_t)b * P.pages_per_seq + i];
+    const int32_t* btg = P.block_table + (size_t)b * P.pages_per_seq;
+    constexpr int PV_UNROLL = 8;
+    uint4 kpre[NSC];                   // the cached K row this thread currently holds (position k_held)
+    uint2 kspre = make_uint2(0u, 0u);
+    int k_held = -1;
+    if (tid < seqlen) {
+        k_held = tid;
+        const int page = btg[tid / P.page_size];
+        const size_t row = ((size_t)page * P.page_size + tid % P.page_size) * P.KVH + kvh;
+#pragma unroll
+        for (int blk = 0; blk < NSC; ++blk) kpre[blk] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + blk);
+        if constexpr (NSC == 4) kspre = __ldg(reinterpret_cast<const uint2*>(P.k_s + row * NSC));
+        else kspre.x = __ldg(reinterpret_cast<const uint32_t*>(P.k_s + row * NSC));
+    }
+    uint32_t vpre[PV_UNROLL];          // packed nibbles of my VEC values | fp16 scale << 16
+#pragma unroll
+    for (int u = 0; u < PV_UNROLL; ++u) {
+        const int p = warp + u * AQ_WARPS;
+        vpre[u] = 0x8888u;
+        if (p < seqlen) {
+            const int page = btg[p / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
+            uint32_t x;
+            if constexpr (VEC == 4) x = __ldg(reinterpret_cast<const uint16_t*>(P.v_q + row * ROWB + lane * 2));
+            else x = (uint32_t)__ldg(P.v_q + row * ROWB + lane) | 0x8800u;
+            vpre[u] = x | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(P.v_s + row * NSC + ((lane * VEC) >> 5))) << 16);
+        }
+    }
+    for (int i = tid; i < P.pages_per_seq; i += AQ_THREADS) pages_s[i] = btg[i];
     const int* bt = pages_s;
+    griddep_wait();
 
-    // ---- 1. quantise the new rows (fp16_to_q_kv arithmetic), keep them in shared memory, one CTA per kv head stores them
-    for (int job = warp; job < 2 * P.q_len * UNITS; job += AQ_WARPS) {
+    // ---- 1. quantise the new rows (fp16_to_q_kv arithmetic) on the first warps, keep them in shared memory; at the same
+    //      time the LAST warps rotate the first query: qrot = H q * (softmax_scale * log2 e / 32)
+    auto rotate_q = [&](int i, int un) {
+        const half2 qh = reinterpret_cast<const half2*>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD + un * 64)[lane];
+        float2 w = hadamard32_f(__half22float2(qh), lane);
+        const float f = P.scale_log2 * (1.0f / 32.0f);
+        qrot[un * 64 + 2 * lane] = w.x * f;
+        qrot[un * 64 + 2 * lane + 1] = w.y * f;
+    };
+    if (warp >= AQ_WARPS - UNITS) rotate_q(0, warp - (AQ_WARPS - UNITS));
+    const int n_jobs = 2 * P.q_len * UNITS;
+    for (int job = (warp >= AQ_WARPS - UNITS && n_jobs <= AQ_WARPS - UNITS) ? n_jobs : warp; job < n_jobs; job += AQ_WARPS) {
         const int kv = job / (P.q_len * UNITS), r = job - kv * P.q_len * UNITS;
         const int i = r / UNITS, un = r - i * UNITS;
         const half* src = (kv ? P.v_new : P.k_new) + (((size_t)b * P.q_len + i) * P.KVH + kvh) * HD + un * 64;
@@ -139,21 +181,44 @@ __global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_consta
         }
     }
 
+    // score of one cached row held in registers (4-bit values against the rotated query)
+    auto score_row = [&](const uint4* kq4, uint2 ks2) {
+        float s = 0.f;
+        const half* ksh = reinterpret_cast<const half*>(&ks2);
+#pragma unroll
+        for (int blk = 0; blk < NSC; ++blk) {
+            const uint32_t ww[4] = {kq4[blk].x, kq4[blk].y, kq4[blk].z, kq4[blk].w};
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 qa = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8);
+                const float4 qb = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8 + 4);
+                const uint32_t x = ww[j];
+                a0 = fmaf(nib_f(x & 15u), qa.x, a0);
+                a1 = fmaf(nib_f((x >> 4) & 15u), qa.y, a1);
+                a0 = fmaf(nib_f((x >> 8) & 15u), qa.z, a0);
+                a1 = fmaf(nib_f((x >> 12) & 15u), qa.w, a1);
+                a0 = fmaf(nib_f((x >> 16) & 15u), qb.x, a0);
+                a1 = fmaf(nib_f((x >> 20) & 15u), qb.y, a1);
+                a0 = fmaf(nib_f((x >> 24) & 15u), qb.z, a0);
+                a1 = fmaf(nib_f(x >> 28), qb.w, a1);
+            }
+            s = fmaf(__half2float(ksh[blk]), a0 + a1, s);
+        }
+        return s;
+    };
+
     for (int i = 0; i < P.q_len; ++i) {
         const int n_ctx = seqlen + i + 1;
-        // ---- 2. rotate the query once: qrot = H q * (softmax_scale * log2 e / 32) ----
-        if (warp < UNITS) {
-            const half2 qh = reinterpret_cast<const half2*>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD + warp * 64)[lane];
-            float2 w = hadamard32_f(__half22float2(qh), lane);
-            const float f = P.scale_log2 * (1.0f / 32.0f);
-            qrot[warp * 64 + 2 * lane] = w.x * f;
-            qrot[warp * 64 + 2 * lane + 1] = w.y * f;
+        if (i > 0) {                         // (the first query was rotated above, next to the quantisation)
+            if (warp < UNITS) rotate_q(i, warp);
+            __syncthreads();
         }
-        __syncthreads();
 
-        // ---- 3. scores: one position per thread, the whole (rotated) row against qrot ----
+        // ---- 2. scores: one position per thread, the whole (rotated) row against qrot ----
         float lmax = -INFINITY;
         for (int p = tid; p < n_ctx; p += AQ_THREADS) {
+            float s;
             if (p >= seqlen) {                   // a row appended by this step: fp16 values, rotated in fp32
                 const float* y = new_y + (p - seqlen) * HD;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -164,36 +229,18 @@ __global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_consta
                     s2 = fmaf(qrot[j + 2], y[j + 2], s2);
                     s3 = fmaf(qrot[j + 3], y[j + 3], s3);
                 }
-                const float s = (s0 + s1) + (s2 + s3);
-                sc[p] = s;
-                lmax = fmaxf(lmax, s);
-                continue;
-            }
-            const int page = bt[p / P.page_size];
-            const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
-            const uint8_t* kq = P.k_q + row * ROWB;
-            const half* ks = P.k_s + row * NSC;
-            float s = 0.f;
+                s = (s0 + s1) + (s2 + s3);
+            } else {
+                if (p != k_held) {               // (the first row of every thread was fetched before the dependency wait)
+                    const int page = bt[p / P.page_size];
+                    const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
 #pragma unroll
-            for (int blk = 0; blk < NSC; ++blk) {
-                const uint4 w4 = *reinterpret_cast<const uint4*>(kq + blk * 16);
-                const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
-                float a = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 qa = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8);
-                    const float4 qb = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8 + 4);
-                    const uint32_t x = ww[j];
-                    a = fmaf(nib_f(x & 15u), qa.x, a);
-                    a = fmaf(nib_f((x >> 4) & 15u), qa.y, a);
-                    a = fmaf(nib_f((x >> 8) & 15u), qa.z, a);
-                    a = fmaf(nib_f((x >> 12) & 15u), qa.w, a);
-                    a = fmaf(nib_f((x >> 16) & 15u), qb.x, a);
-                    a = fmaf(nib_f((x >> 20) & 15u), qb.y, a);
-                    a = fmaf(nib_f((x >> 24) & 15u), qb.z, a);
-                    a = fmaf(nib_f(x >> 28), qb.w, a);
+                    for (int blk = 0; blk < NSC; ++blk) kpre[blk] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + blk);
+                    if constexpr (NSC == 4) kspre = __ldg(reinterpret_cast<const uint2*>(P.k_s + row * NSC));
+                    else kspre.x = __ldg(reinterpret_cast<const uint32_t*>(P.k_s + row * NSC));
+                    k_held = p;
                 }
-                s = fmaf(__half2float(ks[blk]), a, s);
+                s = score_row(kpre, kspre);
             }
             sc[p] = s;
             lmax = fmaxf(lmax, s);
@@ -219,39 +266,46 @@ __global__ void __launch_bounds__(AQ_THREADS) attn_q4_kernel(const __grid_consta
 #pragma unroll
         for (int w = 0; w < AQ_WARPS; ++w) denom += wred[AQ_WARPS + w];
 
-        // ---- 4. P V in the rotated domain: lane = VEC consecutive values, warps stride over positions ----
+        // ---- 3. P V in the rotated domain: lane = VEC consecutive values, warps stride over positions ----
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-        constexpr int PV_UNROLL = 8;
-        for (int p0 = warp; p0 < seqlen; p0 += AQ_WARPS * PV_UNROLL) {       // cached rows: all loads of 8 positions in flight
-            uint32_t xq[PV_UNROLL];
-            float pe[PV_UNROLL];
+        auto pv_fma = [&](uint32_t xs, float pw) {
+            const float pe = pw * __half2float(__ushort_as_half((unsigned short)(xs >> 16)));
+            if constexpr (VEC == 4) {
+                acc[0] = fmaf(pe, nib_f(xs & 15u), acc[0]);
+                acc[1] = fmaf(pe, nib_f((xs >> 4) & 15u), acc[1]);
+                acc[2] = fmaf(pe, nib_f((xs >> 8) & 15u), acc[2]);
+                acc[3] = fmaf(pe, nib_f((xs >> 12) & 15u), acc[3]);
+            } else {
+                acc[0] = fmaf(pe, nib_f(xs & 15u), acc[0]);
+                acc[1] = fmaf(pe, nib_f((xs >> 4) & 15u), acc[1]);
+            }
+        };
 #pragma unroll
-            for (int u = 0; u < PV_UNROLL; ++u) {
+        for (int u = 0; u < PV_UNROLL; ++u) {                                 // rows prefetched before the dependency wait
+            const int p = warp + u * AQ_WARPS;
+            if (p < seqlen) pv_fma(vpre[u], sc[p]);
+        }
+        for (int p0 = warp + PV_UNROLL * AQ_WARPS; p0 < seqlen; p0 += AQ_WARPS * 8) {   // longer contexts: 8 rows in flight
+            uint32_t xs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
                 const int p = p0 + u * AQ_WARPS;
-                xq[u] = 0x8888u;
-                pe[u] = 0.f;
+                xs[u] = 0x8888u;
                 if (p < seqlen) {
                     const int page = bt[p / P.page_size];
                     const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
-                    if constexpr (VEC == 4) xq[u] = *reinterpret_cast<const uint16_t*>(P.v_q + row * ROWB + lane * 2);
-                    else xq[u] = P.v_q[row * ROWB + lane];
-                    pe[u] = sc[p] * __half2float(P.v_s[row * NSC + ((lane * VEC) >> 5)]);
+                    uint32_t x;
+                    if constexpr (VEC == 4) x = __ldg(reinterpret_cast<const uint16_t*>(P.v_q + row * ROWB + lane * 2));
+                    else x = (uint32_t)__ldg(P.v_q + row * ROWB + lane) | 0x8800u;
+                    xs[u] = x | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(P.v_s + row * NSC + ((lane * VEC) >> 5))) << 16);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < PV_UNROLL; ++u) {
-                const uint32_t x = xq[u];
-                if constexpr (VEC == 4) {
-                    acc[0] = fmaf(pe[u], nib_f(x & 15u), acc[0]);
-                    acc[1] = fmaf(pe[u], nib_f((x >> 4) & 15u), acc[1]);
-                    acc[2] = fmaf(pe[u], nib_f((x >> 8) & 15u), acc[2]);
-                    acc[3] = fmaf(pe[u], nib_f((x >> 12) & 15u), acc[3]);
-                } else {
-                    acc[0] = fmaf(pe[u], nib_f(x & 15u), acc[0]);
-                    acc[1] = fmaf(pe[u], nib_f((x >> 4) & 15u), acc[1]);
-                }
+            for (int u = 0; u < 8; ++u) {
+                const int p = p0 + u * AQ_WARPS;
+                if (p < seqlen) pv_fma(xs[u], sc[p]);
             }
         }
         if (warp == 0) {                                                      // rows appended by this step (<= 8)

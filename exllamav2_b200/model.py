@@ -70,6 +70,9 @@ PRESETS = {
     "llama2-70b-2.5bpw": lambda: LlamaConfig(
         "llama2-70b-2.5bpw", 8192, 28672, 64, 8, 128, 80, 32000,
         plan=QuantPlan(attn=((4, 3), (0.1, 0.9), 128), mlp=[((3, 2), (0.3, 0.7), 64)], head=((6,), (1.0,), 128))),
+    # kv width 512: a token's K/V row is exactly one 512-value cache block, so the reference's block-granular re-quantisation
+    # (cache.cu:177-184) never touches a neighbouring token and the per-row fused kernel must reproduce its cache bit for bit
+    "test-small": lambda: LlamaConfig("test-small", 512, 1408, 8, 8, 64, 2, 512, max_seq_len=512, plan=_mix_4bpw()),
     "test-tiny": lambda: LlamaConfig("test-tiny", 256, 704, 4, 2, 64, 2, 512, max_seq_len=512, plan=_mix_4bpw()),
 }
 

@@ -36,9 +36,9 @@ def test_decoder_sequences_agree(batch):
     g = torch.Generator().manual_seed(5)
     prompt = torch.randint(0, 512, (batch, 11), generator=g).to(DEV)
     gen = torch.randint(0, 512, (batch, 4), generator=g).to(DEV)
-    ref, kq_ref, sl_ref = _run("ref", "test-tiny", prompt, gen, False)
-    fus, kq_fus, sl_fus = _run("fused", "test-tiny", prompt, gen, False)
-    chn, kq_chn, sl_chn = _run("chained", "test-tiny", prompt, gen, False)
+    ref, kq_ref, sl_ref = _run("ref", "test-small", prompt, gen, False)
+    fus, kq_fus, sl_fus = _run("fused", "test-small", prompt, gen, False)
+    chn, kq_chn, sl_chn = _run("chained", "test-small", prompt, gen, False)
     assert np.array_equal(sl_ref, sl_fus) and np.array_equal(sl_ref, sl_chn) and int(sl_ref[0]) == 15
     for t in range(gen.shape[1]):
         assert np.isfinite(chn[t]).all()
@@ -50,6 +50,19 @@ def test_decoder_sequences_agree(batch):
     assert np.array_equal(kq_ref, kq_fus)
     # chained: same bytes except where a rounding difference moved a value across a quantisation step
     assert (kq_chn != kq_ref).mean() < 0.02
+
+
+def test_gqa_narrow_kv_chained_vs_fused():
+    """test-tiny: GQA with a 128-wide kv row (TinyLlama-like).  There the reference re-quantises whole 512-value blocks, i.e.
+    neighbouring tokens, on every append (cache.cu:177-184); the fused kernel quantises each row once -- a documented
+    divergence, so only the two fused host sequences are compared."""
+    g = torch.Generator().manual_seed(8)
+    prompt = torch.randint(0, 512, (1, 9), generator=g).to(DEV)
+    gen = torch.randint(0, 512, (1, 3), generator=g).to(DEV)
+    fus, _, _ = _run("fused", "test-tiny", prompt, gen, False)
+    chn, _, _ = _run("chained", "test-tiny", prompt, gen, False)
+    for a, b in zip(chn, fus):
+        assert np.isfinite(a).all() and oracle.rel_l2(a, b) < 1e-2
 
 
 def test_chained_graph_matches_eager():
