@@ -69,11 +69,13 @@ using namespace exl2b;
 
 extern "C" int exl2b_qattn_create(const exl2b_qattn_desc* d, exl2b_qattn_t* out) {
     EXL2B_REQUIRE(d && out, "null argument");
-    EXL2B_REQUIRE(d->q_proj && d->k_proj && d->v_proj && d->o_proj, "q/k/v/o handles are required");
+    // o_proj may be absent: a tensor-parallel rank runs part 1 on its heads and applies its column shard of o_proj itself
+    // (exllamav2_b200/tensor_p.py), part 2 then is not available on this handle
+    EXL2B_REQUIRE(d->q_proj && d->k_proj && d->v_proj, "q/k/v handles are required");
     const QMatrix *q = (const QMatrix*)d->q_proj, *k = (const QMatrix*)d->k_proj, *v = (const QMatrix*)d->v_proj,
-                  *o = (const QMatrix*)d->o_proj;
+                  *o = d->o_proj ? (const QMatrix*)d->o_proj : q;
     EXL2B_REQUIRE(q->v.K == d->hidden_size && k->v.K == d->hidden_size && v->v.K == d->hidden_size, "q/k/v_proj is wrong shape");
-    EXL2B_REQUIRE(o->v.N == d->hidden_size, "o_proj is wrong shape");          // ext_qattn.cpp:67
+    EXL2B_REQUIRE(!d->o_proj || o->v.N == d->hidden_size, "o_proj is wrong shape");          // ext_qattn.cpp:67
     EXL2B_REQUIRE(q->v.N == d->num_heads * d->head_dim && k->v.N == d->num_kv_heads * d->head_dim && v->v.N == k->v.N,
                   "projection widths do not match the head layout");
     EXL2B_REQUIRE(q->device == k->device && q->device == v->device && q->device == o->device, "handles on different devices");
@@ -140,6 +142,7 @@ extern "C" int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint
                                         int input_prepared, const exl2b_chain_t* next, exl2b_stream_t stream) {
     QAttn* a = (QAttn*)h;
     EXL2B_REQUIRE(a && x && (attn_out || input_prepared), "null argument");
+    EXL2B_REQUIRE(a->d.o_proj, "this attention handle was created without o_proj");
     EXL2B_CUDA(cudaSetDevice(a->device));
     const QMatrix* mo = (const QMatrix*)a->d.o_proj;
     GemvMat m = make_mat(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, a->d.has_residual ? 0 : 1);
@@ -164,12 +167,13 @@ extern "C" int exl2b_qattn_forward_2(exl2b_qattn_t h, uint16_t* x, const uint16_
 
 extern "C" int exl2b_qmlp_create(const exl2b_qmlp_desc* d, exl2b_qmlp_t* out) {
     EXL2B_REQUIRE(d && out, "null argument");
-    EXL2B_REQUIRE(d->gate && d->up && d->down, "gate/up/down handles are required");
-    const QMatrix *g = (const QMatrix*)d->gate, *u = (const QMatrix*)d->up, *dn = (const QMatrix*)d->down;
-    EXL2B_REQUIRE(g->v.K == d->hidden_size && u->v.K == d->hidden_size && dn->v.N == d->hidden_size, "mlp matrices have wrong shape");
-    EXL2B_REQUIRE(g->v.N == d->intermediate_size && u->v.N == d->intermediate_size && dn->v.K == d->intermediate_size,
+    // down may be absent (tensor-parallel rank: gate|up on its intermediate slice, exl2b_qmlp_forward_gateup)
+    EXL2B_REQUIRE(d->gate && d->up, "gate/up handles are required");
+    const QMatrix *g = (const QMatrix*)d->gate, *u = (const QMatrix*)d->up, *dn = d->down ? (const QMatrix*)d->down : nullptr;
+    EXL2B_REQUIRE(g->v.K == d->hidden_size && u->v.K == d->hidden_size && (!dn || dn->v.N == d->hidden_size), "mlp matrices have wrong shape");
+    EXL2B_REQUIRE(g->v.N == d->intermediate_size && u->v.N == d->intermediate_size && (!dn || dn->v.K == d->intermediate_size),
                   "mlp intermediate size mismatch");
-    EXL2B_REQUIRE(g->device == u->device && g->device == dn->device, "handles on different devices");
+    EXL2B_REQUIRE(g->device == u->device && (!dn || g->device == dn->device), "handles on different devices");
     QMlp* m = new QMlp{*d, g->device};
     *out = (exl2b_qmlp_t)m;
     return 0;
@@ -185,6 +189,7 @@ extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint
     (void)temp_b;    // the up projection never materialises: silu(gate)*up is formed in the GEMV epilogue
     QMlp* m = (QMlp*)h;
     EXL2B_REQUIRE(m && x && temp_a, "null argument");
+    EXL2B_REQUIRE(m->d.down, "this MLP handle was created without down_proj");
     cudaStream_t stream = (cudaStream_t)stream_;
     EXL2B_CUDA(cudaSetDevice(m->device));
     const exl2b_qmlp_desc& d = m->d;
@@ -223,6 +228,21 @@ extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint
     rc = chain_in(e2, &down, &dn, 1, false);
     if (rc) return rc;
     return gemv_launch(m->device, stream, &down, 1, rows, nullptr, 0.f, EPI_STORE, &e2);
+}
+
+// first half of the MLP only: temp_a[rows, intermediate] = act(norm(x) @ gate) * (norm(x) @ up)   (x is not modified)
+extern "C" int exl2b_qmlp_forward_gateup(exl2b_qmlp_t h, const uint16_t* x, int rows, uint16_t* temp_a, exl2b_stream_t stream_) {
+    QMlp* m = (QMlp*)h;
+    EXL2B_REQUIRE(m && x && temp_a, "null argument");
+    EXL2B_CUDA(cudaSetDevice(m->device));
+    const exl2b_qmlp_desc& d = m->d;
+    const QMatrix *g = (const QMatrix*)d.gate, *u = (const QMatrix*)d.up;
+    GemvMat gu[2] = {
+        make_mat(g, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
+        make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
+    };
+    return gemv_launch(m->device, (cudaStream_t)stream_, gu, 2, rows, (const half*)d.layernorm, d.norm_epsilon,
+                       d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL);
 }
 
 extern "C" int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b,

@@ -86,6 +86,7 @@ _sig("exl2b_qattn_forward_2", c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
 _sig("exl2b_qmlp_create", c_int, POINTER(_QMlpDesc), POINTER(c_void_p))
 _sig("exl2b_qmlp_destroy", c_int, c_void_p)
 _sig("exl2b_qmlp_forward", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p)
+_sig("exl2b_qmlp_forward_gateup", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p)
 _sig("exl2b_paged_attn_decode_q4", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p]))
 
 
@@ -440,6 +441,13 @@ def q_mlp_forward_(q_mlp: int, x, loras=(), loras_temp=none_tensor):
 
 
 # names the reference's hot-path call sites use that this module provides
+
+def q_mlp_forward_gateup(q_mlp: int, x, temp_a):
+    """temp_a[rows, intermediate] = act(norm(x) @ gate) * (norm(x) @ up) -- the first half of q_mlp_forward_, used by a
+    tensor-parallel rank on its intermediate slice (ext_qmlp.cpp:326-473)."""
+    rows = x.numel() // x.shape[-1]
+    _check(lib.exl2b_qmlp_forward_gateup(q_mlp, x.data_ptr(), rows, temp_a.data_ptr(), _stream(x)))
+
 
 def make_chain(consumers, norm_weight=None) -> "_Chain":
     """Describe who reads a launch's output: `consumers` = q_handles of the matrices fed by it, `norm_weight` = the

@@ -143,6 +143,12 @@ typedef struct exl2b_qmlp_desc {
 int exl2b_qmlp_create(const exl2b_qmlp_desc* desc, exl2b_qmlp_t* out);
 int exl2b_qmlp_destroy(exl2b_qmlp_t h);
 int exl2b_qmlp_forward(exl2b_qmlp_t h, uint16_t* x, int rows, uint16_t* temp_a, uint16_t* temp_b, exl2b_stream_t stream);
+/* Column-sharded (tensor-parallel) use, exllamav2/tensor_p.py + ext_qattn.cpp:261-732 / ext_qmlp.cpp:326-473 in the
+ * reference: a rank creates the attention block with ITS heads (num_heads / num_kv_heads = local counts) and o_proj = NULL,
+ * the MLP block with ITS intermediate columns and down = NULL, runs part 1 / the gate|up half locally, all-gathers the
+ * sharded activation, and applies its column shard of o_proj / down with exl2b_gemm_half_q_half(clear = 0) into its slice of
+ * the residual stream (ldc = hidden size). */
+int exl2b_qmlp_forward_gateup(exl2b_qmlp_t h, const uint16_t* x, int rows, uint16_t* temp_a, exl2b_stream_t stream);
 
 /* ---- host-buffer entry point (bench.py "e2e"): a fp16[M,K] and c fp16[M,N] are HOST pointers (pinned or
  * pageable); the call copies a to the device, runs gemm_half_q_half, copies c back and waits. */
