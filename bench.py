@@ -89,6 +89,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
 
 
+_CPU_MATS: dict = {}
+
+
 def cpu_port_baseline(cfg, budget_s: float = 12.0) -> dict:
     """Time oracle/exl2_cpu.c (fused CPU dequant-GEMV over the checkpoint layout) on ONE decoder layer's seven
     matrices (1/num_layers of the layer weights), all host threads; extrapolate to tokens/s."""
@@ -115,8 +118,10 @@ def cpu_port_baseline(cfg, budget_s: float = 12.0) -> dict:
                     perm=rng.permutation(K).astype(np.uint16), K=K, N=N, G=G, R=row)
 
     mp = cfg.plan.mlp[0]
-    mats = [rand_exl2(hid, H * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn),
+    cached = _CPU_MATS.get(cfg.name)
+    mats = cached if cached is not None else [rand_exl2(hid, H * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn), rand_exl2(hid, KVH * hd, cfg.plan.attn),
             rand_exl2(H * hd, hid, cfg.plan.attn), rand_exl2(hid, inter, mp), rand_exl2(hid, inter, mp), rand_exl2(inter, hid, mp)]
+    _CPU_MATS[cfg.name] = mats
     ins = [rng.normal(size=(m["K"],)).astype(np.float32) for m in mats]
     outs = [np.empty((m["N"],), dtype=np.float32) for m in mats]
 
@@ -294,8 +299,19 @@ def run_ours(args, rank, world):
     ms_gemv = e0.elapsed_time(e1) / R
     peak, peak_src = measured_peaks()
     achieved = dec.weight_bytes / (ms_gemv * 1e-3) / 1e9
+    # DRAM traffic of the kernel from the committed ncu capture (profiles/): measured bytes of one launch of a known shape;
+    # scaled by this run's algorithmic bytes per launch it says how much is re-read (ratio ~1.00: nothing)
+    traffic, traffic_note = None, "no ncu capture committed"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_tc_traffic.json")) as f:
+            tj = json.load(f)
+        ratio = tj["dram_bytes_per_launch"] / tj["algorithmic_bytes_per_launch"]
+        traffic = ratio * dec.weight_bytes / n_gemv
+        traffic_note = f"ncu dram__bytes_read+write / algorithmic = {ratio:.3f} on {tj['shape']} ({tj['source']}), applied to this run's mean launch"
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_token": dec.weight_bytes,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_token": dec.weight_bytes,
                 "gemv_launches_per_token": n_gemv, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
                 "note": f"{n_launch_roof} launches ({n_gemv} dequant-GEMMs + their prep/rope launches, if any) replayed back to back in one CUDA graph, CUDA events"}
 
