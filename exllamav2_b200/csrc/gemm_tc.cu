@@ -706,6 +706,27 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
         TC_STAMP(4);
 
+        // the finishing CTA's scatter needs, per consumer, this column's destination row and RMSNorm weight: request them now, so
+        // that the loads ride under the combine / split-K hand-off below instead of sitting on the tail of the launch
+        int skp[GEMV_MAX_MATS];
+        half ssc[GEMV_MAX_MATS];
+        half resid0 = __float2half(0.f);            // decode (one row): the residual element this column adds to, same idea
+        if constexpr (MT == 1) {
+            if (rwg == 0 && P.epilogue == EPI_STORE && !mt.clear && n_col < w.N) resid0 = mt.c[n_col];
+        }
+        {
+            const bool col_any = n_col < ((P.epilogue != EPI_STORE) ? P.mat[0].w.N : w.N);
+#pragma unroll
+            for (int t = 0; t < GEMV_MAX_MATS; ++t) {
+                skp[t] = n_col;
+                ssc[t] = __float2half(1.f);
+                if (rwg == 0 && t < P.ex.num_scat && col_any) {
+                    if (P.ex.scat[t].invperm) skp[t] = (int)__ldg(P.ex.scat[t].invperm + n_col);
+                    if (P.ex.scat[t].scale) ssc[t] = __ldg(P.ex.scat[t].scale + n_col);
+                }
+            }
+        }
+
         // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
         __syncthreads();
         if (rwg == 1) {
@@ -804,7 +825,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     float v = fin[m] * rs;
                     if (col_ok && m < M) {
                         if (w.bias) v += __half2float(w.bias[n_col]);
-                        if (!mt.clear) v += __half2float(mt.c[(size_t)m * mt.ldc + n_col]);
+                        if (!mt.clear) v += __half2float(MT == 1 ? resid0 : mt.c[(size_t)m * mt.ldc + n_col]);
                     }
                     hv[m] = __float2half_rn(v);
                 }
@@ -847,11 +868,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     mo.c[(size_t)m * mo.ldc + n_col] = hv[m];
                     const float f = fmaxf(-65504.f, fminf(__half2float(hv[m]), 65504.f));
                     ssq[m] = f * f;
-                    for (int t = 0; t < P.ex.num_scat; ++t) {
-                        const ScatterTarget& T = P.ex.scat[t];
-                        const int kp = T.invperm ? (int)__ldg(T.invperm + n_col) : n_col;
-                        const half o = T.scale ? __float2half_rn(f * __half2float(__ldg(T.scale + n_col))) : hv[m];
-                        T.xp[(size_t)(kp >> 3) * 64 + m * 8 + (kp & 7)] = o;
+#pragma unroll
+                    for (int t = 0; t < GEMV_MAX_MATS; ++t) {
+                        if (t < P.ex.num_scat) {
+                            const ScatterTarget& T = P.ex.scat[t];
+                            const int kp = skp[t];
+                            const half o = T.scale ? __float2half_rn(f * __half2float(ssc[t])) : hv[m];
+                            T.xp[(size_t)(kp >> 3) * 64 + m * 8 + (kp & 7)] = o;
+                        }
                     }
                 }
             }
