@@ -974,9 +974,10 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
         const long long L = (units + grid_ll - 1) / grid_ll;
         const long long cost_stream = ((L + P.KS - 1) / P.KS + 1) * F + L;
         if (strips <= slots) {
-            int S = (int)(slots / strips);
-            while (S > 1 && (P.KS % S) != 0) --S;
-            const long long cost_aligned = F + P.KS / S;
+            // S need not divide KS: CTA i covers units [i*U/G, (i+1)*U/G), every S-th boundary is a strip boundary, the others
+            // are snapped to quantisation-group starts by the kernel -- still exactly one segment per CTA
+            const int S = (int)std::min<long long>(slots / strips, std::max(1, P.KS / 8));
+            const long long cost_aligned = F + (P.KS + S - 1) / S;
             if (cost_aligned <= cost_stream) grid_ll = (long long)strips * S;
         }
     }
