@@ -1,4 +1,4 @@
-"""Lock-step comparison of the chained and unchained layer loops on test-tiny (debug aid)."""
+"""Lock-step comparison of the chained and un-chained layer loops on test-tiny, stage by stage (diagnostics)."""
 import math, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
