@@ -291,590 +291,6 @@ __global__ void __launch_bounds__(1024) tc_prep_kernel(const __grid_constant__ P
     }
 }
 
-
-// Per-CTA state of the dequant-GEMM pipeline that outlives a segment: thread roles, shared-memory carve-up, barrier
-// parities, tensor-memory addresses.  tc_segment() below runs ONE segment (matrix, strip, K-range) against it; the launch
-// kernel calls it for its unit range, a persistent kernel would call it phase after phase.
-struct TcCtx {
-    int tid, lane, warp, wg, rwg, wq, tidw;
-    bool is_mma;
-    int stage_bytes, NS, M, KS;
-    uint32_t wbar, abar, barA, barD, barF, act_ring, ring, lane_sel;
-    uint8_t* smem;
-    uint8_t* ring_p;
-    uint32_t* tmem_slot;
-    int* flag_s;
-    float *rstd_s, *comb_s, *ssq_s, *corr_s;
-    half* tile_s;
-    unsigned U, G;
-    bool setup_done, waited;
-    uint32_t tmem_base, t_a, t_d;
-    uint32_t wphase, aphase, phaseA, phaseD, phaseF, ab, a_uses, dsel;
-};
-
-template <int MT>
-__device__ __forceinline__ int tc_segment(const GemvParams& P, TcCtx& c, const int u, const int u1) {
-    const int tid = c.tid, lane = c.lane, warp = c.warp, wg = c.wg, rwg = c.rwg, wq = c.wq, tidw = c.tidw;
-    const bool is_mma = c.is_mma;
-    const int stage_bytes = c.stage_bytes, NS = c.NS, M = c.M, KS = c.KS;
-    const uint32_t wbar = c.wbar, abar = c.abar, barA = c.barA, barD = c.barD, barF = c.barF, act_ring = c.act_ring, ring = c.ring, lane_sel = c.lane_sel;
-    uint8_t* const smem = c.smem;
-    uint8_t* const ring_p = c.ring_p;
-    uint32_t* const tmem_slot = c.tmem_slot;
-    int* const flag_s = c.flag_s;
-    float* const rstd_s = c.rstd_s;
-    float* const comb_s = c.comb_s;
-    float* const ssq_s = c.ssq_s;
-    float* const corr_s = c.corr_s;
-    half* const tile_s = c.tile_s;
-    const unsigned U = c.U, G = c.G;
-    bool& setup_done = c.setup_done;
-    bool& waited = c.waited;
-    uint32_t &tmem_base = c.tmem_base, &t_a = c.t_a, &t_d = c.t_d;
-    uint32_t &wphase = c.wphase, &aphase = c.aphase, &phaseA = c.phaseA, &phaseD = c.phaseD, &phaseF = c.phaseF, &ab = c.ab, &a_uses = c.a_uses, &dsel = c.dsel;
-    TCP_DECL
-    auto after_wait = [&]() {       // first point where the previous kernel's output may be read
-        if (P.ex.sumsq_in) {        // warp m: 1/rms of token m, strips summed in a fixed order
-            float sum = 0.f;
-            for (int sidx = lane; sidx < P.ex.sumsq_in_strips; sidx += 32) sum += __ldcg(P.ex.sumsq_in + sidx * 8 + warp);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) rstd_s[warp] = rsqrtf(sum / (float)(KS * SLAB_K) + P.ex.sumsq_eps);
-        }
-    };
-    (void)tid; (void)smem; (void)M;
-    int mi = 0;
-    while (mi + 1 < P.num_mats && u >= P.mat[mi + 1].unit_begin) ++mi;
-    const GemvMat& mt = P.mat[mi];
-    const QMatView& w = mt.w;
-    const int local = u - mt.unit_begin;
-    const int strip = local / KS, ks_a = local - strip * KS;
-    const int seg = min(KS - ks_a, u1 - u);
-    // snap the slab range to group boundaries (every CTA applies the same rule, so ranges still tile the strip);
-    // WG0 takes the first half of the range's groups, WG1 the second: two contiguous streams per CTA
-    const int ks0 = tc_group_start(w, ks_a), ks1 = tc_group_start(w, ks_a + seg);
-    const int ksm = tc_group_start(w, ks0 + ((ks1 - ks0 + 1) >> 1));
-    const int my0 = wg ? ksm : ks0, my1 = wg ? ks1 : ksm;
-    const int n_col = strip * 128 + tidw;                                  // this thread's output column
-    const bool col_live = n_col < w.N;
-    const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
-    const uint8_t* asrc = reinterpret_cast<const uint8_t*>(mt.xp);
-    const int nreg = w.num_regions;
-    // per-matrix fields used in the loops below, pinned in registers (indexed kernel-parameter reads are slow and the
-    // compiler would otherwise re-read them every group)
-    const bool gptq = w.is_gptq != 0;
-    const uint32_t* sc_w = (gptq ? w.qzeros : w.q_scale) + (n_col >> 3);     // my column's nibble word of group 0
-    const half* sc_h = gptq ? w.gptq_scales + n_col : w.q_scale_max;
-    int n8 = w.N >> 3;
-    asm volatile("" : "+l"(sc_w));
-    asm volatile("" : "+l"(sc_h));
-    asm volatile("" : "+r"(n8));
-    const int nib_sh = (n_col & 7) * 4;
-
-    // Group cursors: position + the current region's parameters in registers, so that stepping to the next group
-    // is a handful of integer ops; the kernel-parameter region table is only read when a region boundary is crossed.
-    //   C: the group being unpacked;   F: the next group to request (weights + activations), NS groups ahead
-    int c_ks = my0, c_r = tc_region_of(w, min(my0, KS - 1));
-    int c_bits = w.reg[c_r].bits, c_spg = 1 << w.reg[c_r].spg_log2, c_end = tc_region_end(w, c_r);
-    int c_grp = w.reg[c_r].group_base + ((my0 - w.reg[c_r].ks_begin) >> w.reg[c_r].spg_log2);
-    int f_ks = c_ks, f_r = c_r, f_bits = c_bits, f_spg = c_spg, f_end = c_end;
-    uint32_t f_off = w.reg[c_r].off_base + (uint32_t)(my0 - w.reg[c_r].ks_begin) * (uint32_t)block_bytes(c_bits);
-    int f_stage = 0, cstage = 0;
-
-    // request group F's weights (every warp: its own block) and, optionally, its activations (the WG's first warp)
-    auto issue = [&](bool weights, bool acts) {
-        const int ns = min(f_spg, f_end - f_ks);
-        const uint32_t wbytes = (uint32_t)ns * (uint32_t)block_bytes(f_bits);
-        if (elect_one()) {
-            if (weights) {
-                mbar_arrive_expect_tx(wbar + 8 * f_stage, wbytes);
-                bulk_copy_g2s(ring + f_stage * stage_bytes, gsrc + f_off, wbytes, wbar + 8 * f_stage);
-            }
-            if (acts && wq == 0) {
-                mbar_arrive_expect_tx(abar + 8 * f_stage, (uint32_t)ns * SLAB_K * 16);
-                bulk_copy_g2s(act_ring + f_stage * TC_ACT_STAGE, asrc + (size_t)f_ks * SLAB_K * 16, (uint32_t)ns * SLAB_K * 16,
-                              abar + 8 * f_stage);
-            }
-        }
-        f_ks += ns;
-        f_off += wbytes;
-        f_stage = (f_stage + 1 == NS) ? 0 : f_stage + 1;
-        if (f_ks >= f_end && f_r + 1 < nreg) {
-            ++f_r;
-            f_bits = w.reg[f_r].bits;
-            f_spg = 1 << w.reg[f_r].spg_log2;
-            f_end = tc_region_end(w, f_r);
-            f_off = w.reg[f_r].off_base;
-        }
-    };
-    // prologue: the first NS groups' weights (they never depend on a previous kernel); their activations follow after
-    // griddepcontrol.wait, requested by re-walking the same groups with a scratch copy of the cursor
-    int primed = 0;
-#pragma unroll 1
-    for (; !is_mma && primed < NS && f_ks < my1; ++primed) issue(true, false);
-    if (!setup_done) {
-        setup_done = true;
-        if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        tmem_base = *tmem_slot;
-        t_a = tmem_base + wg * TC_COLS_PER_WG;          // A: 3 x 32 columns, D: 2 x 16
-        t_d = t_a + TC_A_BUFS * 32;
-    }
-    TC_STAMP(1);
-
-    if (is_mma) {
-        // ---- tensor-core issue warp of warpgroup wg: for every chunk wait until the four unpack warps have filled the
-        //      A buffer, issue its MMAs (2 per slab, K = 16), commit to "A buffer free" (+ "accumulator complete" at the
-        //      group's last chunk).  It never blocks the unpack warps: they only meet it through mbarriers.
-        int m_ks = my0, m_r = c_r, m_spg = c_spg, m_end = c_end, m_bits = c_bits, mstage = 0;
-        while (m_ks < my1) {
-            const int ns = min(m_spg, m_end - m_ks);
-            const int nchunks = (ns + 1) >> 1;
-            TCP_BEGIN;
-            mbar_wait(abar + 8 * mstage, (aphase >> mstage) & 1u);       // the group's activations have landed
-            aphase ^= 1u << mstage;
-            TCP_END(0);
-            const uint8_t* actp = smem + P.tc_act_off + (wg * NS + mstage) * TC_ACT_STAGE;
-#pragma unroll 1
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int nsl = min(2, ns - 2 * ch);
-                TCP_BEGIN;
-                mbar_wait(barF + 8 * ab, (phaseF >> ab) & 1u);
-                phaseF ^= 1u << ab;
-                tc_fence_after();
-                TCP_END(0);
-                if (ch == 0) {
-                    // (all four unpack warps are past the read-back of the group that last used this stage's S1 / S0)
-                    if (m_bits == 4) {
-                        // lane = (token t, k-quarter kq): sums over the 8-k core-matrix rows 4*kq .. 4*kq+3 of every slab
-                        const int t = lane & 7, kq = lane >> 3;
-                        float s1 = 0.f, s0 = 0.f;
-                        for (int row = kq; row < ns * 4; row += 4) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(actp + row * 128 + t * 16);
-                            const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const half2*>(&v.y));
-                            const float2 f2 = __half22float2(*reinterpret_cast<const half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const half2*>(&v.w));
-                            const float e = (f0.x + f0.y) + (f2.x + f2.y), o = (f1.x + f1.y) + (f3.x + f3.y);   // even / odd pair slots
-                            s1 = fmaf(1024.f, e, fmaf(64.f, o, s1));
-                            s0 += e + o;
-                        }
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                        if (lane < 8) {
-                            corr_s[mstage * 16 + lane] = s1;
-                            corr_s[mstage * 16 + 8 + lane] = s0;
-                        }
-                    }
-                    __syncwarp();
-                    if (elect_one()) mbar_arrive(barD + 8 * dsel);
-                }
-                TCP_END(1);
-                // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
-                const uint64_t bd0 = make_b_desc(act_ring + mstage * TC_ACT_STAGE + (uint32_t)ch * 1024u);
-                const uint32_t td = t_d + dsel * 16, ta = t_a + ab * 32;
-                if (elect_one()) {
-                    if (nsl == 2) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
-                    }
-#ifdef EXL2B_TC_PROFILE
-                }
-                __syncwarp();
-                TCP_END(2);
-                if (elect_one()) {
-#endif
-                    umma_commit(barA + 8 * ab);
-                    if (ch == nchunks - 1) umma_commit(barD + 8 * dsel);
-                }
-                __syncwarp();
-                TCP_END(3);
-                ab = (ab == 2u) ? 0u : ab + 1u;
-            }
-            dsel ^= 1u;
-            mstage = (mstage + 1 == NS) ? 0 : mstage + 1;
-            m_ks += ns;
-            if (m_ks >= m_end && m_r + 1 < nreg) {
-                ++m_r;
-                m_spg = 1 << w.reg[m_r].spg_log2;
-                m_end = tc_region_end(w, m_r);
-                m_bits = w.reg[m_r].bits;
-            }
-        }
-    }
-
-
-    // everything above depended only on the weights; from here on the previous kernel's output is needed
-    if (!waited && !is_mma) {
-        griddep_wait();
-        waited = true;
-        after_wait();
-        TC_STAMP(2);
-    }
-    if (!is_mma && wq == 0) {            // the activations of the groups primed above (same walk, scratch cursor)
-        int t_ks = my0, t_r = c_r, t_spg = c_spg, t_end = c_end;
-        for (int st = 0; st < primed; ++st) {
-            const int tn = min(t_spg, t_end - t_ks);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(abar + 8 * st, (uint32_t)tn * SLAB_K * 16);
-                bulk_copy_g2s(act_ring + st * TC_ACT_STAGE, asrc + (size_t)t_ks * SLAB_K * 16, (uint32_t)tn * SLAB_K * 16, abar + 8 * st);
-            }
-            t_ks += tn;
-            if (t_ks >= t_end && t_r + 1 < nreg) {
-                ++t_r;
-                t_spg = 1 << w.reg[t_r].spg_log2;
-                t_end = tc_region_end(w, t_r);
-            }
-        }
-    }
-
-    // ---- the unpack pipeline of a warp.  Per chunk (<= 2 slabs = 64 k): wait for a free A buffer -> unpack ->
-    //      tcgen05.st -> arrive on "A full"; the issue warp does the rest.  The accumulator of group g is read back
-    //      (tcgen05.ld, scaled, added) only after group g+1 has been unpacked, so tensor core and unpack overlap.
-    float tot[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) tot[m] = 0.f;
-    bool pending = false;
-    // State of a group between its unpack and its read-back.  Two instances used alternately (the loop below is unrolled
-    // by two): a scale loaded at the top of group g is first touched when g is read back, at the END of group g+1 -- no
-    // register move in between that would make the in-order warp wait for the load.
-    struct GroupState {
-        uint32_t word;       // raw q_scale word (EXL2)
-        half h;              // q_scale_max[group] (EXL2) / scale of (group, column) (GPTQ)
-        int z;               // zero point when unpacked in two-offset form (EXL2: 8, GPTQ: z + 1), -1: exact unpack
-        uint32_t d;          // accumulator index
-        int stage;           // pipeline stage (where the issue warp left S1 / S0)
-    };
-    GroupState ga = {0u, __float2half(0.f), -1, 0u, 0}, gb = ga;
-    uint32_t zw_next = 0;            // GPTQ: qzeros word of the NEXT group, fetched a group ahead
-    if (!is_mma && gptq && col_live && c_ks < my1) zw_next = __ldg(sc_w + (size_t)c_grp * n8);
-
-    auto drain = [&](const GroupState& g) {       // accumulator of group g -> running totals; its stage gets the next request
-        const uint32_t d = g.d;
-        mbar_wait(barD + 8 * d, (phaseD >> d) & 1u);
-        phaseD ^= 1u << d;
-        tc_fence_after();
-        TCP_END(2);
-        float pend_scale = 0.f;
-        if (col_live) {
-            if (!gptq) {
-                const int nib = (int)((g.word >> nib_sh) & 15u);
-                pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), g.h));    // qdq_util.cuh:24-30
-            } else {
-                pend_scale = __half2float(g.h);
-            }
-        }
-        float dd[MT];
-        if constexpr (MT == 1) tmem_ld1(t_d + d * 16 + lane_sel, dd[0]);
-        else tmem_ld8(t_d + d * 16 + lane_sel, dd);
-        if (g.z >= 0) {              // remove the unpack offsets and the zero point
-            const float zf = (float)g.z;
-            const float* cs = corr_s + g.stage * 16;
-            tmem_wait_ld();
-#pragma unroll
-            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m] - fmaf(zf, cs[8 + m], cs[m]), tot[m]);
-        } else {
-            tmem_wait_ld();
-#pragma unroll
-            for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m], tot[m]);
-        }
-        tc_fence_before();
-        if (f_ks < my1) issue(true, true);       // the drained group's MMAs have retired: both of its stages are free
-    };
-
-    auto group_step = [&](GroupState& cur, const GroupState& prev) {
-        const int bits = c_bits;
-        const int ns = min(c_spg, c_end - c_ks);
-        const int grp = c_grp;
-
-        // (a) this group's scale for my column: requested now, decoded when the group is read back
-        cur.word = 0u;
-        cur.h = __float2half(0.f);
-        cur.z = bits == 4 ? 8 : -1;
-        if (col_live) {
-            if (!gptq) {
-                cur.word = __ldg(sc_w + (size_t)grp * n8);
-                cur.h = __ldg(sc_h + grp);
-            } else {
-                cur.h = __ldg(sc_h + (size_t)grp * (n8 * 8));
-                cur.z = (int)((zw_next >> nib_sh) & 15u) + 1;                                   // q_gemm_kernel_gptq.cuh:167-172
-                if (c_ks + ns < my1) zw_next = __ldg(sc_w + (size_t)(grp + 1) * n8);           // GPTQ: one region
-            }
-        }
-        cur.d = dsel;
-        cur.stage = cstage;
-
-        // (b) my block's slabs of this group have landed
-        TCP_BEGIN;
-        mbar_wait(wbar + 8 * cstage, (wphase >> cstage) & 1u);
-        wphase ^= 1u << cstage;
-        TCP_END(0);
-        const uint8_t* sp = ring_p + cstage * stage_bytes;
-        const int nchunks = (ns + 1) >> 1;
-        auto run_chunks = [&](auto tag) {
-            constexpr int B = decltype(tag)::value;
-#pragma unroll 1
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int nsl = min(2, ns - 2 * ch);
-                TCP_BEGIN;
-                if (a_uses >= 3u) {              // the MMAs that read this A buffer three chunks ago have retired
-                    mbar_wait(barA + 8 * ab, (phaseA >> ab) & 1u);
-                    phaseA ^= 1u << ab;
-                    tc_fence_after();
-                }
-                TCP_END(0);
-                tc_dequant_chunk<B>(sp, 2 * ch, nsl, lane, t_a + ab * 32 + lane_sel);
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (elect_one()) mbar_arrive(barF + 8 * ab);     // 1 of 4: this warp's 32 rows of the A buffer are in place
-                ab = (ab == 2u) ? 0u : ab + 1u;
-                ++a_uses;
-                TCP_END(1);
-            }
-        };
-        switch (bits) {
-            case 4: run_chunks(std::integral_constant<int, 4>{}); break;
-            case 5: run_chunks(std::integral_constant<int, 5>{}); break;
-            case 3: run_chunks(std::integral_constant<int, 3>{}); break;
-            case 6: run_chunks(std::integral_constant<int, 6>{}); break;
-            case 2: run_chunks(std::integral_constant<int, 2>{}); break;
-            default: run_chunks(std::integral_constant<int, 8>{}); break;
-        }
-        // (c) read back the PREVIOUS group while this one's MMAs run (and re-arm its stage), then step the cursor
-        TCP_BEGIN;
-        if (pending) drain(prev);
-        TCP_END(3);
-        pending = true;
-        dsel ^= 1u;
-        cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
-        c_ks += ns;
-        ++c_grp;
-        if (c_ks >= c_end && c_r + 1 < nreg) {
-            ++c_r;
-            c_bits = w.reg[c_r].bits;
-            c_spg = 1 << w.reg[c_r].spg_log2;
-            c_end = tc_region_end(w, c_r);
-            c_grp = w.reg[c_r].group_base;
-        }
-    };
-    bool last_a = false;
-    while (!is_mma && c_ks < my1) {
-        group_step(ga, gb);
-        last_a = true;
-        if (c_ks >= my1) break;
-        group_step(gb, ga);
-        last_a = false;
-    }
-    if (pending) {
-        if (last_a) drain(ga);
-        else drain(gb);
-    }
-    if (!waited && !is_mma) {        // a CTA whose snapped range is empty still takes part in the fix-up below
-        griddep_wait();
-        waited = true;
-        after_wait();
-    }
-    TC_STAMP(4);
-
-    // the finishing CTA's scatter needs, per consumer, this column's destination row and RMSNorm weight: request them now, so
-    // that the loads ride under the combine / split-K hand-off below instead of sitting on the tail of the launch
-    int skp[GEMV_MAX_MATS];
-    half ssc[GEMV_MAX_MATS];
-    half resid0 = __float2half(0.f);            // decode (one row): the residual element this column adds to, same idea
-    if constexpr (MT == 1) {
-        if (rwg == 0 && P.epilogue == EPI_STORE && !mt.clear && n_col < w.N) resid0 = mt.c[n_col];
-    }
-    {
-        const bool col_any = n_col < ((P.epilogue != EPI_STORE) ? P.mat[0].w.N : w.N);
-#pragma unroll
-        for (int t = 0; t < GEMV_MAX_MATS; ++t) {
-            skp[t] = n_col;
-            ssc[t] = __float2half(1.f);
-            if (rwg == 0 && t < P.ex.num_scat && col_any) {
-                if (P.ex.scat[t].invperm) skp[t] = (int)__ldg(P.ex.scat[t].invperm + n_col);
-                if (P.ex.scat[t].scale) ssc[t] = __ldg(P.ex.scat[t].scale + n_col);
-            }
-        }
-    }
-
-    // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
-    __syncthreads();
-    if (rwg == 1) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) comb_s[m * 128 + tidw] = tot[m];
-    }
-    __syncthreads();
-
-    const int gs = mt.strip_begin + strip;
-    const unsigned sb = (unsigned)mt.unit_begin + (unsigned)strip * KS;
-    const int first_cta = tc_cta_of_unit(sb, G, U), last_cta = tc_cta_of_unit(sb + KS - 1, G, U);
-    const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
-    const bool paired = P.epilogue != EPI_STORE;
-    const bool has_rstd = P.ex.sumsq_in != nullptr;
-    if (rwg == 0) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) tot[m] += comb_s[m * 128 + tidw];
-    }
-    // fin / fin2: the strip's complete fp32 sums (fin2 = the up projection of a gate/up pair), held by the finishing CTA
-    bool finisher = false;
-    float fin[MT], fin2[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) { fin[m] = tot[m]; fin2[m] = 0.f; }
-    if (nc == 1 && !paired) {
-        finisher = true;
-    } else {
-        float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * TC_RED_FLOATS;
-        if (rwg == 0) {
-#pragma unroll
-            for (int m = 0; m < MT; ++m) __stcg(wsp + m * 128 + tidw, tot[m]);
-        }
-        __syncthreads();             // every partial of this CTA is written (CTA-scope happens-before to thread 0)
-        int expected = nc, cidx = gs;
-        if (paired) {
-            const GemvMat& other = P.mat[1 - mi];
-            const unsigned ob = (unsigned)other.unit_begin + (unsigned)strip * KS;
-            expected += tc_cta_of_unit(ob + KS - 1, G, U) - tc_cta_of_unit(ob, G, U) + 1;
-            cidx = P.mat[0].strip_begin + strip;
-        }
-        if (tid == 0) {              // release our partials / acquire everybody else's: one acq_rel RMW at GPU scope
-            unsigned int old;
-            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(P.counters + cidx), "r"(1u) : "memory");
-            *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
-        }
-        __syncthreads();
-        if (*flag_s) {
-            finisher = true;
-            if (rwg == 0) {
-                if (!paired) {
-                    const float* base = P.ws + (size_t)gs * P.maxc * TC_RED_FLOATS;
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        float v = 0.f;
-                        for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
-                        fin[m] = v;
-                    }
-                } else {
-                    const GemvMat& mg = P.mat[0];
-                    const GemvMat& mu = P.mat[1];
-                    const unsigned gb = (unsigned)mg.unit_begin + (unsigned)strip * KS;
-                    const unsigned ub = (unsigned)mu.unit_begin + (unsigned)strip * KS;
-                    const int ncg = tc_cta_of_unit(gb + KS - 1, G, U) - tc_cta_of_unit(gb, G, U) + 1;
-                    const int ncu = tc_cta_of_unit(ub + KS - 1, G, U) - tc_cta_of_unit(ub, G, U) + 1;
-                    const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
-                    const float* bu = P.ws + (size_t)(mu.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        float vg = 0.f, vu = 0.f;
-                        for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
-                        for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
-                        fin[m] = vg;
-                        fin2[m] = vu;
-                    }
-                }
-            }
-            if (tid == 0) P.counters[cidx] = 0u;
-        }
-    }
-
-    // ---- the finishing CTA's first warpgroup turns the sums into outputs (thread = column) ----
-    if (finisher && rwg == 0) {
-        const GemvMat& mo = paired ? P.mat[0] : mt;         // where the result goes
-        const bool col_ok = n_col < mo.w.N;
-        half hv[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const float rs = has_rstd ? rstd_s[m] : 1.f;
-            if (paired) {
-                float vg = fin[m] * rs, vu = fin2[m] * rs;
-                if (col_ok && P.mat[0].w.bias) vg += __half2float(P.mat[0].w.bias[n_col]);
-                if (col_ok && P.mat[1].w.bias) vu += __half2float(P.mat[1].w.bias[n_col]);
-                const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);           // q_mlp.cu:187-196 roundings
-                const half act = (P.epilogue == EPI_GELU_MUL) ? tc_gelu_h(hg) : tc_silu_h(hg);
-                hv[m] = __hmul(act, hu);
-            } else {
-                float v = fin[m] * rs;
-                if (col_ok && m < M) {
-                    if (w.bias) v += __half2float(w.bias[n_col]);
-                    if (!mt.clear) v += __half2float(MT == 1 ? resid0 : mt.c[(size_t)m * mt.ldc + n_col]);
-                }
-                hv[m] = __float2half_rn(v);
-            }
-        }
-        if ((P.ex.rope.mask >> mi) & 1u) {          // RoPE on the fp16 values, partner through shared memory
-            const RopeFuse& R = P.ex.rope;
-#pragma unroll
-            for (int m = 0; m < MT; ++m) tile_s[m * 128 + tidw] = hv[m];
-            bar_sync(3, 128);
-            const int d = tidw % R.head_dim, S = R.sincos_size, hd2 = S >> 1;
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                if (m < M && d < S) {
-                    const int row = P.row0 + m, bb = row / R.q_len, tt = row - bb * R.q_len;
-                    int base = R.past_len;
-                    if (base == -1) base = max(R.past_lens[bb], 0);
-                    else if (R.past_lens) base += R.past_lens[bb];
-                    const size_t sr = (size_t)max(base + tt, 0) * S;
-                    if (R.neox) {
-                        if (d < hd2) {
-                            const half c = R.cos[sr + d], sn = R.sin[sr + d];
-                            hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw + hd2], __hneg(sn)));
-                        } else {
-                            const half c = R.cos[sr + d - hd2], sn = R.sin[sr + d - hd2];
-                            hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw - hd2], sn));
-                        }
-                    } else {
-                        const half c = R.cos[sr + d], sn = R.sin[sr + d];
-                        if ((d & 1) == 0) hv[m] = __hfma(tile_s[m * 128 + tidw + 1], __hneg(sn), __hmul(hv[m], c));
-                        else hv[m] = __hfma(tile_s[m * 128 + tidw - 1], sn, __hmul(hv[m], c));
-                    }
-                }
-            }
-        }
-        float ssq[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            ssq[m] = 0.f;
-            if (col_ok && m < M) {
-                mo.c[(size_t)m * mo.ldc + n_col] = hv[m];
-                const float f = fmaxf(-65504.f, fminf(__half2float(hv[m]), 65504.f));
-                ssq[m] = f * f;
-#pragma unroll
-                for (int t = 0; t < GEMV_MAX_MATS; ++t) {
-                    if (t < P.ex.num_scat) {
-                        const ScatterTarget& T = P.ex.scat[t];
-                        const int kp = skp[t];
-                        const half o = T.scale ? __float2half_rn(f * __half2float(ssc[t])) : hv[m];
-                        T.xp[(size_t)(kp >> 3) * 64 + m * 8 + (kp & 7)] = o;
-                    }
-                }
-            }
-        }
-        if (P.ex.sumsq_out) {        // per-strip sum of squares of the stored rows, fixed reduction order
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], o);
-                if (lane == 0) ssq_s[wq * 8 + m] = ssq[m];
-            }
-            bar_sync(3, 128);
-            if (tidw < 8) {
-                const float t4 = (ssq_s[tidw] + ssq_s[8 + tidw]) + (ssq_s[16 + tidw] + ssq_s[24 + tidw]);
-                P.ex.sumsq_out[(size_t)strip * 8 + tidw] = (tidw < MT) ? t4 : 0.f;
-            }
-        }
-    }
-    __syncthreads();
-    TC_STAMP(5);
-    TCP_FLUSH;
-    return seg;
-}
-
 template <int MT>   // MT = 1 (decode) or 8 tokens per pass
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -928,25 +344,564 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     __syncwarp();
     // (a warp's weight barriers are used by that warp alone: it may start fetching right away; the tensor-memory allocation
     //  and the CTA-wide barrier that publishes the shared barriers come after the first requests are in flight)
+    bool setup_done = false;
+    uint32_t tmem_base = 0, t_a = 0, t_d = 0;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
 
     const unsigned U = (unsigned)P.total_units, G = gridDim.x;
     const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
 
-    TcCtx c;
-    c.tid = tid; c.lane = lane; c.warp = warp; c.wg = wg; c.rwg = rwg; c.wq = wq; c.tidw = tidw; c.is_mma = is_mma;
-    c.stage_bytes = stage_bytes; c.NS = NS; c.M = M; c.KS = KS;
-    c.wbar = wbar; c.abar = abar; c.barA = barA; c.barD = barD; c.barF = barF; c.act_ring = act_ring; c.ring = ring; c.lane_sel = lane_sel;
-    c.smem = smem; c.ring_p = ring_p; c.tmem_slot = tmem_slot; c.flag_s = flag_s; c.rstd_s = rstd_s; c.comb_s = comb_s; c.ssq_s = ssq_s;
-    c.corr_s = corr_s; c.tile_s = tile_s; c.U = U; c.G = G;
-    c.setup_done = false; c.waited = false; c.tmem_base = 0; c.t_a = 0; c.t_d = 0;
-    c.wphase = c.aphase = c.phaseA = c.phaseD = c.phaseF = 0; c.ab = c.a_uses = c.dsel = 0;
+    uint32_t wphase = 0, aphase = 0, phaseA = 0, phaseD = 0, phaseF = 0;     // parity bits per barrier
+    TCP_DECL
+    uint32_t ab = 0, a_uses = 0, dsel = 0;                        // A buffer / accumulator rotation of this WG (across segments)
+    bool waited = false;
+    auto after_wait = [&]() {       // first point where the previous kernel's output may be read
+        if (P.ex.sumsq_in) {        // warp m: 1/rms of token m, strips summed in a fixed order
+            float sum = 0.f;
+            for (int sidx = lane; sidx < P.ex.sumsq_in_strips; sidx += 32) sum += __ldcg(P.ex.sumsq_in + sidx * 8 + warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) rstd_s[warp] = rsqrtf(sum / (float)(KS * SLAB_K) + P.ex.sumsq_eps);
+        }
+    };
+
     int u = u0;
-    while (u < u1) u += tc_segment<MT>(P, c, u, u1);
+    while (u < u1) {
+        int mi = 0;
+        while (mi + 1 < P.num_mats && u >= P.mat[mi + 1].unit_begin) ++mi;
+        const GemvMat& mt = P.mat[mi];
+        const QMatView& w = mt.w;
+        const int local = u - mt.unit_begin;
+        const int strip = local / KS, ks_a = local - strip * KS;
+        const int seg = min(KS - ks_a, u1 - u);
+        // snap the slab range to group boundaries (every CTA applies the same rule, so ranges still tile the strip);
+        // WG0 takes the first half of the range's groups, WG1 the second: two contiguous streams per CTA
+        const int ks0 = tc_group_start(w, ks_a), ks1 = tc_group_start(w, ks_a + seg);
+        const int ksm = tc_group_start(w, ks0 + ((ks1 - ks0 + 1) >> 1));
+        const int my0 = wg ? ksm : ks0, my1 = wg ? ks1 : ksm;
+        const int n_col = strip * 128 + tidw;                                  // this thread's output column
+        const bool col_live = n_col < w.N;
+        const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes + (size_t)wq * w.blk_stream_bytes;
+        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(mt.xp);
+        const int nreg = w.num_regions;
+        // per-matrix fields used in the loops below, pinned in registers (indexed kernel-parameter reads are slow and the
+        // compiler would otherwise re-read them every group)
+        const bool gptq = w.is_gptq != 0;
+        const uint32_t* sc_w = (gptq ? w.qzeros : w.q_scale) + (n_col >> 3);     // my column's nibble word of group 0
+        const half* sc_h = gptq ? w.gptq_scales + n_col : w.q_scale_max;
+        int n8 = w.N >> 3;
+        asm volatile("" : "+l"(sc_w));
+        asm volatile("" : "+l"(sc_h));
+        asm volatile("" : "+r"(n8));
+        const int nib_sh = (n_col & 7) * 4;
+
+        // Group cursors: position + the current region's parameters in registers, so that stepping to the next group
+        // is a handful of integer ops; the kernel-parameter region table is only read when a region boundary is crossed.
+        //   C: the group being unpacked;   F: the next group to request (weights + activations), NS groups ahead
+        int c_ks = my0, c_r = tc_region_of(w, min(my0, KS - 1));
+        int c_bits = w.reg[c_r].bits, c_spg = 1 << w.reg[c_r].spg_log2, c_end = tc_region_end(w, c_r);
+        int c_grp = w.reg[c_r].group_base + ((my0 - w.reg[c_r].ks_begin) >> w.reg[c_r].spg_log2);
+        int f_ks = c_ks, f_r = c_r, f_bits = c_bits, f_spg = c_spg, f_end = c_end;
+        uint32_t f_off = w.reg[c_r].off_base + (uint32_t)(my0 - w.reg[c_r].ks_begin) * (uint32_t)block_bytes(c_bits);
+        int f_stage = 0, cstage = 0;
+
+        // request group F's weights (every warp: its own block) and, optionally, its activations (the WG's first warp)
+        auto issue = [&](bool weights, bool acts) {
+            const int ns = min(f_spg, f_end - f_ks);
+            const uint32_t wbytes = (uint32_t)ns * (uint32_t)block_bytes(f_bits);
+            if (elect_one()) {
+                if (weights) {
+                    mbar_arrive_expect_tx(wbar + 8 * f_stage, wbytes);
+                    bulk_copy_g2s(ring + f_stage * stage_bytes, gsrc + f_off, wbytes, wbar + 8 * f_stage);
+                }
+                if (acts && wq == 0) {
+                    mbar_arrive_expect_tx(abar + 8 * f_stage, (uint32_t)ns * SLAB_K * 16);
+                    bulk_copy_g2s(act_ring + f_stage * TC_ACT_STAGE, asrc + (size_t)f_ks * SLAB_K * 16, (uint32_t)ns * SLAB_K * 16,
+                                  abar + 8 * f_stage);
+                }
+            }
+            f_ks += ns;
+            f_off += wbytes;
+            f_stage = (f_stage + 1 == NS) ? 0 : f_stage + 1;
+            if (f_ks >= f_end && f_r + 1 < nreg) {
+                ++f_r;
+                f_bits = w.reg[f_r].bits;
+                f_spg = 1 << w.reg[f_r].spg_log2;
+                f_end = tc_region_end(w, f_r);
+                f_off = w.reg[f_r].off_base;
+            }
+        };
+        // prologue: the first NS groups' weights (they never depend on a previous kernel); their activations follow after
+        // griddepcontrol.wait, requested by re-walking the same groups with a scratch copy of the cursor
+        int primed = 0;
+#pragma unroll 1
+        for (; !is_mma && primed < NS && f_ks < my1; ++primed) issue(true, false);
+        if (!setup_done) {
+            setup_done = true;
+            if (warp == 0) tmem_alloc(smem_addr(tmem_slot), TC_TMEM_COLS);
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            tmem_base = *tmem_slot;
+            t_a = tmem_base + wg * TC_COLS_PER_WG;          // A: 3 x 32 columns, D: 2 x 16
+            t_d = t_a + TC_A_BUFS * 32;
+        }
+        TC_STAMP(1);
+
+        if (is_mma) {
+            // ---- tensor-core issue warp of warpgroup wg: for every chunk wait until the four unpack warps have filled the
+            //      A buffer, issue its MMAs (2 per slab, K = 16), commit to "A buffer free" (+ "accumulator complete" at the
+            //      group's last chunk).  It never blocks the unpack warps: they only meet it through mbarriers.
+            int m_ks = my0, m_r = c_r, m_spg = c_spg, m_end = c_end, m_bits = c_bits, mstage = 0;
+            while (m_ks < my1) {
+                const int ns = min(m_spg, m_end - m_ks);
+                const int nchunks = (ns + 1) >> 1;
+                TCP_BEGIN;
+                mbar_wait(abar + 8 * mstage, (aphase >> mstage) & 1u);       // the group's activations have landed
+                aphase ^= 1u << mstage;
+                TCP_END(0);
+                const uint8_t* actp = smem + P.tc_act_off + (wg * NS + mstage) * TC_ACT_STAGE;
+#pragma unroll 1
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int nsl = min(2, ns - 2 * ch);
+                    TCP_BEGIN;
+                    mbar_wait(barF + 8 * ab, (phaseF >> ab) & 1u);
+                    phaseF ^= 1u << ab;
+                    tc_fence_after();
+                    TCP_END(0);
+                    if (ch == 0) {
+                        // (all four unpack warps are past the read-back of the group that last used this stage's S1 / S0)
+                        if (m_bits == 4) {
+                            // lane = (token t, k-quarter kq): sums over the 8-k core-matrix rows 4*kq .. 4*kq+3 of every slab
+                            const int t = lane & 7, kq = lane >> 3;
+                            float s1 = 0.f, s0 = 0.f;
+                            for (int row = kq; row < ns * 4; row += 4) {
+                                const uint4 v = *reinterpret_cast<const uint4*>(actp + row * 128 + t * 16);
+                                const float2 f0 = __half22float2(*reinterpret_cast<const half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const half2*>(&v.y));
+                                const float2 f2 = __half22float2(*reinterpret_cast<const half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const half2*>(&v.w));
+                                const float e = (f0.x + f0.y) + (f2.x + f2.y), o = (f1.x + f1.y) + (f3.x + f3.y);   // even / odd pair slots
+                                s1 = fmaf(1024.f, e, fmaf(64.f, o, s1));
+                                s0 += e + o;
+                            }
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                            if (lane < 8) {
+                                corr_s[mstage * 16 + lane] = s1;
+                                corr_s[mstage * 16 + 8 + lane] = s0;
+                            }
+                        }
+                        __syncwarp();
+                        if (elect_one()) mbar_arrive(barD + 8 * dsel);
+                    }
+                    TCP_END(1);
+                    // K-step j: A advances 8 TMEM columns, B advances 2 core matrices = 256 B = 16 descriptor units
+                    const uint64_t bd0 = make_b_desc(act_ring + mstage * TC_ACT_STAGE + (uint32_t)ch * 1024u);
+                    const uint32_t td = t_d + dsel * 16, ta = t_a + ab * 32;
+                    if (elect_one()) {
+                        if (nsl == 2) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) umma_ts(td, ta + j * 8, bd0 + (uint64_t)(j * 16), TC_IDESC, (ch | j) ? 1u : 0u);
+                        }
+#ifdef EXL2B_TC_PROFILE
+                    }
+                    __syncwarp();
+                    TCP_END(2);
+                    if (elect_one()) {
+#endif
+                        umma_commit(barA + 8 * ab);
+                        if (ch == nchunks - 1) umma_commit(barD + 8 * dsel);
+                    }
+                    __syncwarp();
+                    TCP_END(3);
+                    ab = (ab == 2u) ? 0u : ab + 1u;
+                }
+                dsel ^= 1u;
+                mstage = (mstage + 1 == NS) ? 0 : mstage + 1;
+                m_ks += ns;
+                if (m_ks >= m_end && m_r + 1 < nreg) {
+                    ++m_r;
+                    m_spg = 1 << w.reg[m_r].spg_log2;
+                    m_end = tc_region_end(w, m_r);
+                    m_bits = w.reg[m_r].bits;
+                }
+            }
+        }
+
+
+        // everything above depended only on the weights; from here on the previous kernel's output is needed
+        if (!waited && !is_mma) {
+            griddep_wait();
+            waited = true;
+            after_wait();
+            TC_STAMP(2);
+        }
+        if (!is_mma && wq == 0) {            // the activations of the groups primed above (same walk, scratch cursor)
+            int t_ks = my0, t_r = c_r, t_spg = c_spg, t_end = c_end;
+            for (int st = 0; st < primed; ++st) {
+                const int tn = min(t_spg, t_end - t_ks);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(abar + 8 * st, (uint32_t)tn * SLAB_K * 16);
+                    bulk_copy_g2s(act_ring + st * TC_ACT_STAGE, asrc + (size_t)t_ks * SLAB_K * 16, (uint32_t)tn * SLAB_K * 16, abar + 8 * st);
+                }
+                t_ks += tn;
+                if (t_ks >= t_end && t_r + 1 < nreg) {
+                    ++t_r;
+                    t_spg = 1 << w.reg[t_r].spg_log2;
+                    t_end = tc_region_end(w, t_r);
+                }
+            }
+        }
+
+        // ---- the unpack pipeline of a warp.  Per chunk (<= 2 slabs = 64 k): wait for a free A buffer -> unpack ->
+        //      tcgen05.st -> arrive on "A full"; the issue warp does the rest.  The accumulator of group g is read back
+        //      (tcgen05.ld, scaled, added) only after group g+1 has been unpacked, so tensor core and unpack overlap.
+        float tot[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tot[m] = 0.f;
+        bool pending = false;
+        // State of a group between its unpack and its read-back.  Two instances used alternately (the loop below is unrolled
+        // by two): a scale loaded at the top of group g is first touched when g is read back, at the END of group g+1 -- no
+        // register move in between that would make the in-order warp wait for the load.
+        struct GroupState {
+            uint32_t word;       // raw q_scale word (EXL2)
+            half h;              // q_scale_max[group] (EXL2) / scale of (group, column) (GPTQ)
+            int z;               // zero point when unpacked in two-offset form (EXL2: 8, GPTQ: z + 1), -1: exact unpack
+            uint32_t d;          // accumulator index
+            int stage;           // pipeline stage (where the issue warp left S1 / S0)
+        };
+        GroupState ga = {0u, __float2half(0.f), -1, 0u, 0}, gb = ga;
+        uint32_t zw_next = 0;            // GPTQ: qzeros word of the NEXT group, fetched a group ahead
+        if (!is_mma && gptq && col_live && c_ks < my1) zw_next = __ldg(sc_w + (size_t)c_grp * n8);
+
+        auto drain = [&](const GroupState& g) {       // accumulator of group g -> running totals; its stage gets the next request
+            const uint32_t d = g.d;
+            mbar_wait(barD + 8 * d, (phaseD >> d) & 1u);
+            phaseD ^= 1u << d;
+            tc_fence_after();
+            TCP_END(2);
+            float pend_scale = 0.f;
+            if (col_live) {
+                if (!gptq) {
+                    const int nib = (int)((g.word >> nib_sh) & 15u);
+                    pend_scale = __half2float(__hmul(__int2half_rn((nib + 1) * (nib + 1)), g.h));    // qdq_util.cuh:24-30
+                } else {
+                    pend_scale = __half2float(g.h);
+                }
+            }
+            float dd[MT];
+            if constexpr (MT == 1) tmem_ld1(t_d + d * 16 + lane_sel, dd[0]);
+            else tmem_ld8(t_d + d * 16 + lane_sel, dd);
+            if (g.z >= 0) {              // remove the unpack offsets and the zero point
+                const float zf = (float)g.z;
+                const float* cs = corr_s + g.stage * 16;
+                tmem_wait_ld();
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m] - fmaf(zf, cs[8 + m], cs[m]), tot[m]);
+            } else {
+                tmem_wait_ld();
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tot[m] = fmaf(pend_scale, dd[m], tot[m]);
+            }
+            tc_fence_before();
+            if (f_ks < my1) issue(true, true);       // the drained group's MMAs have retired: both of its stages are free
+        };
+
+        auto group_step = [&](GroupState& cur, const GroupState& prev) {
+            const int bits = c_bits;
+            const int ns = min(c_spg, c_end - c_ks);
+            const int grp = c_grp;
+
+            // (a) this group's scale for my column: requested now, decoded when the group is read back
+            cur.word = 0u;
+            cur.h = __float2half(0.f);
+            cur.z = bits == 4 ? 8 : -1;
+            if (col_live) {
+                if (!gptq) {
+                    cur.word = __ldg(sc_w + (size_t)grp * n8);
+                    cur.h = __ldg(sc_h + grp);
+                } else {
+                    cur.h = __ldg(sc_h + (size_t)grp * (n8 * 8));
+                    cur.z = (int)((zw_next >> nib_sh) & 15u) + 1;                                   // q_gemm_kernel_gptq.cuh:167-172
+                    if (c_ks + ns < my1) zw_next = __ldg(sc_w + (size_t)(grp + 1) * n8);           // GPTQ: one region
+                }
+            }
+            cur.d = dsel;
+            cur.stage = cstage;
+
+            // (b) my block's slabs of this group have landed
+            TCP_BEGIN;
+            mbar_wait(wbar + 8 * cstage, (wphase >> cstage) & 1u);
+            wphase ^= 1u << cstage;
+            TCP_END(0);
+            const uint8_t* sp = ring_p + cstage * stage_bytes;
+            const int nchunks = (ns + 1) >> 1;
+            auto run_chunks = [&](auto tag) {
+                constexpr int B = decltype(tag)::value;
+#pragma unroll 1
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int nsl = min(2, ns - 2 * ch);
+                    TCP_BEGIN;
+                    if (a_uses >= 3u) {              // the MMAs that read this A buffer three chunks ago have retired
+                        mbar_wait(barA + 8 * ab, (phaseA >> ab) & 1u);
+                        phaseA ^= 1u << ab;
+                        tc_fence_after();
+                    }
+                    TCP_END(0);
+                    tc_dequant_chunk<B>(sp, 2 * ch, nsl, lane, t_a + ab * 32 + lane_sel);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(barF + 8 * ab);     // 1 of 4: this warp's 32 rows of the A buffer are in place
+                    ab = (ab == 2u) ? 0u : ab + 1u;
+                    ++a_uses;
+                    TCP_END(1);
+                }
+            };
+            switch (bits) {
+                case 4: run_chunks(std::integral_constant<int, 4>{}); break;
+                case 5: run_chunks(std::integral_constant<int, 5>{}); break;
+                case 3: run_chunks(std::integral_constant<int, 3>{}); break;
+                case 6: run_chunks(std::integral_constant<int, 6>{}); break;
+                case 2: run_chunks(std::integral_constant<int, 2>{}); break;
+                default: run_chunks(std::integral_constant<int, 8>{}); break;
+            }
+            // (c) read back the PREVIOUS group while this one's MMAs run (and re-arm its stage), then step the cursor
+            TCP_BEGIN;
+            if (pending) drain(prev);
+            TCP_END(3);
+            pending = true;
+            dsel ^= 1u;
+            cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
+            c_ks += ns;
+            ++c_grp;
+            if (c_ks >= c_end && c_r + 1 < nreg) {
+                ++c_r;
+                c_bits = w.reg[c_r].bits;
+                c_spg = 1 << w.reg[c_r].spg_log2;
+                c_end = tc_region_end(w, c_r);
+                c_grp = w.reg[c_r].group_base;
+            }
+        };
+        bool last_a = false;
+        while (!is_mma && c_ks < my1) {
+            group_step(ga, gb);
+            last_a = true;
+            if (c_ks >= my1) break;
+            group_step(gb, ga);
+            last_a = false;
+        }
+        if (pending) {
+            if (last_a) drain(ga);
+            else drain(gb);
+        }
+        if (!waited && !is_mma) {        // a CTA whose snapped range is empty still takes part in the fix-up below
+            griddep_wait();
+            waited = true;
+            after_wait();
+        }
+        TC_STAMP(4);
+
+        // the finishing CTA's scatter needs, per consumer, this column's destination row and RMSNorm weight: request them now, so
+        // that the loads ride under the combine / split-K hand-off below instead of sitting on the tail of the launch
+        int skp[GEMV_MAX_MATS];
+        half ssc[GEMV_MAX_MATS];
+        half resid0 = __float2half(0.f);            // decode (one row): the residual element this column adds to, same idea
+        if constexpr (MT == 1) {
+            if (rwg == 0 && P.epilogue == EPI_STORE && !mt.clear && n_col < w.N) resid0 = mt.c[n_col];
+        }
+        {
+            const bool col_any = n_col < ((P.epilogue != EPI_STORE) ? P.mat[0].w.N : w.N);
+#pragma unroll
+            for (int t = 0; t < GEMV_MAX_MATS; ++t) {
+                skp[t] = n_col;
+                ssc[t] = __float2half(1.f);
+                if (rwg == 0 && t < P.ex.num_scat && col_any) {
+                    if (P.ex.scat[t].invperm) skp[t] = (int)__ldg(P.ex.scat[t].invperm + n_col);
+                    if (P.ex.scat[t].scale) ssc[t] = __ldg(P.ex.scat[t].scale + n_col);
+                }
+            }
+        }
+
+        // ---- combine the two warpgroups, then the split-K / epilogue logic of the mma.sync kernel ----
+        __syncthreads();
+        if (rwg == 1) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) comb_s[m * 128 + tidw] = tot[m];
+        }
+        __syncthreads();
+
+        const int gs = mt.strip_begin + strip;
+        const unsigned sb = (unsigned)mt.unit_begin + (unsigned)strip * KS;
+        const int first_cta = tc_cta_of_unit(sb, G, U), last_cta = tc_cta_of_unit(sb + KS - 1, G, U);
+        const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
+        const bool paired = P.epilogue != EPI_STORE;
+        const bool has_rstd = P.ex.sumsq_in != nullptr;
+        if (rwg == 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) tot[m] += comb_s[m * 128 + tidw];
+        }
+        // fin / fin2: the strip's complete fp32 sums (fin2 = the up projection of a gate/up pair), held by the finishing CTA
+        bool finisher = false;
+        float fin[MT], fin2[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { fin[m] = tot[m]; fin2[m] = 0.f; }
+        if (nc == 1 && !paired) {
+            finisher = true;
+        } else {
+            float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * TC_RED_FLOATS;
+            if (rwg == 0) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) __stcg(wsp + m * 128 + tidw, tot[m]);
+            }
+            __syncthreads();             // every partial of this CTA is written (CTA-scope happens-before to thread 0)
+            int expected = nc, cidx = gs;
+            if (paired) {
+                const GemvMat& other = P.mat[1 - mi];
+                const unsigned ob = (unsigned)other.unit_begin + (unsigned)strip * KS;
+                expected += tc_cta_of_unit(ob + KS - 1, G, U) - tc_cta_of_unit(ob, G, U) + 1;
+                cidx = P.mat[0].strip_begin + strip;
+            }
+            if (tid == 0) {              // release our partials / acquire everybody else's: one acq_rel RMW at GPU scope
+                unsigned int old;
+                asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(P.counters + cidx), "r"(1u) : "memory");
+                *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (*flag_s) {
+                finisher = true;
+                if (rwg == 0) {
+                    if (!paired) {
+                        const float* base = P.ws + (size_t)gs * P.maxc * TC_RED_FLOATS;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            float v = 0.f;
+                            for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            fin[m] = v;
+                        }
+                    } else {
+                        const GemvMat& mg = P.mat[0];
+                        const GemvMat& mu = P.mat[1];
+                        const unsigned gb = (unsigned)mg.unit_begin + (unsigned)strip * KS;
+                        const unsigned ub = (unsigned)mu.unit_begin + (unsigned)strip * KS;
+                        const int ncg = tc_cta_of_unit(gb + KS - 1, G, U) - tc_cta_of_unit(gb, G, U) + 1;
+                        const int ncu = tc_cta_of_unit(ub + KS - 1, G, U) - tc_cta_of_unit(ub, G, U) + 1;
+                        const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
+                        const float* bu = P.ws + (size_t)(mu.strip_begin + strip) * P.maxc * TC_RED_FLOATS;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            float vg = 0.f, vu = 0.f;
+                            for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * TC_RED_FLOATS + m * 128 + tidw);
+                            fin[m] = vg;
+                            fin2[m] = vu;
+                        }
+                    }
+                }
+                if (tid == 0) P.counters[cidx] = 0u;
+            }
+        }
+
+        // ---- the finishing CTA's first warpgroup turns the sums into outputs (thread = column) ----
+        if (finisher && rwg == 0) {
+            const GemvMat& mo = paired ? P.mat[0] : mt;         // where the result goes
+            const bool col_ok = n_col < mo.w.N;
+            half hv[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const float rs = has_rstd ? rstd_s[m] : 1.f;
+                if (paired) {
+                    float vg = fin[m] * rs, vu = fin2[m] * rs;
+                    if (col_ok && P.mat[0].w.bias) vg += __half2float(P.mat[0].w.bias[n_col]);
+                    if (col_ok && P.mat[1].w.bias) vu += __half2float(P.mat[1].w.bias[n_col]);
+                    const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);           // q_mlp.cu:187-196 roundings
+                    const half act = (P.epilogue == EPI_GELU_MUL) ? tc_gelu_h(hg) : tc_silu_h(hg);
+                    hv[m] = __hmul(act, hu);
+                } else {
+                    float v = fin[m] * rs;
+                    if (col_ok && m < M) {
+                        if (w.bias) v += __half2float(w.bias[n_col]);
+                        if (!mt.clear) v += __half2float(MT == 1 ? resid0 : mt.c[(size_t)m * mt.ldc + n_col]);
+                    }
+                    hv[m] = __float2half_rn(v);
+                }
+            }
+            if ((P.ex.rope.mask >> mi) & 1u) {          // RoPE on the fp16 values, partner through shared memory
+                const RopeFuse& R = P.ex.rope;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tile_s[m * 128 + tidw] = hv[m];
+                bar_sync(3, 128);
+                const int d = tidw % R.head_dim, S = R.sincos_size, hd2 = S >> 1;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    if (m < M && d < S) {
+                        const int row = P.row0 + m, bb = row / R.q_len, tt = row - bb * R.q_len;
+                        int base = R.past_len;
+                        if (base == -1) base = max(R.past_lens[bb], 0);
+                        else if (R.past_lens) base += R.past_lens[bb];
+                        const size_t sr = (size_t)max(base + tt, 0) * S;
+                        if (R.neox) {
+                            if (d < hd2) {
+                                const half c = R.cos[sr + d], sn = R.sin[sr + d];
+                                hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw + hd2], __hneg(sn)));
+                            } else {
+                                const half c = R.cos[sr + d - hd2], sn = R.sin[sr + d - hd2];
+                                hv[m] = __hfma(hv[m], c, __hmul(tile_s[m * 128 + tidw - hd2], sn));
+                            }
+                        } else {
+                            const half c = R.cos[sr + d], sn = R.sin[sr + d];
+                            if ((d & 1) == 0) hv[m] = __hfma(tile_s[m * 128 + tidw + 1], __hneg(sn), __hmul(hv[m], c));
+                            else hv[m] = __hfma(tile_s[m * 128 + tidw - 1], sn, __hmul(hv[m], c));
+                        }
+                    }
+                }
+            }
+            float ssq[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                ssq[m] = 0.f;
+                if (col_ok && m < M) {
+                    mo.c[(size_t)m * mo.ldc + n_col] = hv[m];
+                    const float f = fmaxf(-65504.f, fminf(__half2float(hv[m]), 65504.f));
+                    ssq[m] = f * f;
+#pragma unroll
+                    for (int t = 0; t < GEMV_MAX_MATS; ++t) {
+                        if (t < P.ex.num_scat) {
+                            const ScatterTarget& T = P.ex.scat[t];
+                            const int kp = skp[t];
+                            const half o = T.scale ? __float2half_rn(f * __half2float(ssc[t])) : hv[m];
+                            T.xp[(size_t)(kp >> 3) * 64 + m * 8 + (kp & 7)] = o;
+                        }
+                    }
+                }
+            }
+            if (P.ex.sumsq_out) {        // per-strip sum of squares of the stored rows, fixed reduction order
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], o);
+                    if (lane == 0) ssq_s[wq * 8 + m] = ssq[m];
+                }
+                bar_sync(3, 128);
+                if (tidw < 8) {
+                    const float t4 = (ssq_s[tidw] + ssq_s[8 + tidw]) + (ssq_s[16 + tidw] + ssq_s[24 + tidw]);
+                    P.ex.sumsq_out[(size_t)strip * 8 + tidw] = (tidw < MT) ? t4 : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        TC_STAMP(5);
+        TCP_FLUSH;
+        u += seg;
+    }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(c.tmem_base, TC_TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
     if (P.dbg && tid == 0) atomicMax(P.dbg + 7, tc_gtimer());
 }
 
