@@ -33,7 +33,8 @@ def group_plan(K: int, bits, bits_prop, group_size) -> list[tuple[int, int]]:
 
 def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, device="cuda:0", seed: int = 0,
                 perm: bool = True, weight_std: float | None = None) -> dict:
-    """Random EXL2 tensors.  weight_std: target standard deviation of the dequantised weights (1/sqrt(K) keeps a
+    """Random EXL2 tensors.  weight_std: nominal standard deviation of the dequantised weights -- the realised one is
+    ~1.4x larger because scale nibbles are uniform, see tests/test_synthetic.py -- (1/sqrt(K) keeps a
     random-init network's activations O(1), like a trained checkpoint's ~0.02 at K = 4096); None: scale_max in
     [0.5, 4) stored units, i.e. weights of magnitude ~5 (fine for single-matrix tests, overflows fp16 in a deep stack)."""
     gen = torch.Generator(device=device)

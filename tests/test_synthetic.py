@@ -23,7 +23,9 @@ def test_random_exl2_weight_std(bits, prop, gs):
     wn["q_groups"] = wn["q_groups"].astype(np.int16)
     W = oracle.exl2_reconstruct(wn).astype(np.float64)
     assert W.shape == (K, N) and np.isfinite(W).all()
-    assert 0.75 * target < W.std() < 1.3 * target, (W.std(), target)
+    # weight_std is the nominal knob: the generator sizes q_scale_max from E[(s+1)^2] = 93.5, while the spread of the product
+    # follows sqrt(E[(s+1)^4]) = 123.5, so the realised std is ~1.3-1.45x the nominal value (same for every matrix)
+    assert 0.9 * target < W.std() < 1.6 * target, (W.std(), target)
     assert abs(W.mean()) < 0.3 * target                         # q - 2^(b-1) spans [-2^(b-1), 2^(b-1) - 1]: mean -0.5 steps
     # byte accounting used for the roofline: packed rows * N * 4 + scale words + scale_max + perm + one activation row + one output row
     b = synthetic.algorithmic_bytes(w, 1)
