@@ -8,6 +8,7 @@
 // All launches carry the programmatic-dependent-launch attribute, so a whole decode step captured in one CUDA
 // graph (exllamav2_b200/model.py) streams weights back to back.
 #include "gemv.cuh"
+#include "gemv_i8.cuh"
 
 namespace exl2b {
 
@@ -17,10 +18,13 @@ int rope_launch(cudaStream_t stream, half* x, const half* sin, const half* cos, 
 struct QAttn {
     exl2b_qattn_desc d;
     int device;
+    bool i8_qkv;          // q/k/v share K and the row permutation: one gemv_i8 launch for a single row
 };
 struct QMlp {
     exl2b_qmlp_desc d;
     int device;
+    bool i8_gu;           // same for gate/up
+    half* up_scratch;     // single-row up projection when the caller passes no temp_b (reference: temp_b of make_q_mlp)
 };
 
 static GemvMat make_mat(const QMatrix* q, const half* x, int ldx, half* c, int ldc, int clear) {
@@ -79,7 +83,8 @@ extern "C" int exl2b_qattn_create(const exl2b_qattn_desc* d, exl2b_qattn_t* out)
     EXL2B_REQUIRE(q->v.N == d->num_heads * d->head_dim && k->v.N == d->num_kv_heads * d->head_dim && v->v.N == k->v.N,
                   "projection widths do not match the head layout");
     EXL2B_REQUIRE(q->device == k->device && q->device == v->device && q->device == o->device, "handles on different devices");
-    QAttn* a = new QAttn{*d, q->device};
+    const QMatrix* qkv[3] = {q, k, v};
+    QAttn* a = new QAttn{*d, q->device, gemv_i8_fusable(qkv, 3)};
     *out = (exl2b_qattn_t)a;
     return 0;
 }
@@ -106,6 +111,20 @@ extern "C" int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int 
     };
     const bool rope = d.rope_style != 0;
     if (rope) EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
+    if (rows == 1 && !input_prepared && a->i8_qkv && gemv_i8_enabled()) {
+        // decode row: RMSNorm is the GEMV's prologue, Q|K|V are one launch (gemv_i8.cu); RoPE as in the reference
+        // (q_attn.cu:271-300) -- model.py's decode step instead lets the attention kernel rotate q / k as it reads them
+        const I8Out o[3] = {{mq, (half*)q, 1}, {mk, (half*)k, 1}, {mv, (half*)v, 1}};
+        const I8Input in = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN};
+        int rc = gemv_i8_launch(a->device, stream, o, 3, in);
+        if (rc || !rope || past_len == -2) return rc;          // past_len == -2: caller applies RoPE itself (fused attention)
+        const int neox = d.rope_style == 2;
+        rc = rope_launch(stream, (half*)q, (const half*)sin, (const half*)cos, batch, q_len * d.num_heads, d.head_dim, d.num_heads,
+                         past_len, past_lens, neox, d.sincos_size);
+        if (rc) return rc;
+        return rope_launch(stream, (half*)k, (const half*)sin, (const half*)cos, batch, q_len * d.num_kv_heads, d.head_dim,
+                           d.num_kv_heads, past_len, past_lens, neox, d.sincos_size);
+    }
     const bool fuse = gemv_supports_extras(mats, 3, rows) && (!rope || (d.head_dim <= 128 && 128 % d.head_dim == 0 && d.sincos_size <= d.head_dim));
     EXL2B_REQUIRE(!input_prepared || fuse, "input_prepared needs the tcgen05 layout and at most %d rows", GEMV_MTOK);
     if (fuse) {
@@ -147,6 +166,11 @@ extern "C" int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint
     const QMatrix* mo = (const QMatrix*)a->d.o_proj;
     GemvMat m = make_mat(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, a->d.has_residual ? 0 : 1);
     const bool want = input_prepared || (next && next->num_consumers > 0);
+    if (!want && batch * q_len == 1 && mo->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
+        const I8Out o = {mo, (half*)x, a->d.has_residual ? 0 : 1};
+        const I8Input in = {(const half*)attn_out, nullptr, nullptr, 0.f, I8_PLAIN};
+        return gemv_i8_launch(a->device, (cudaStream_t)stream, &o, 1, in);
+    }
     if (!want) return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
     EXL2B_REQUIRE(gemv_supports_extras(&m, 1, batch * q_len), "chained launches need the tcgen05 layout and at most %d rows", GEMV_MTOK);
     GemvExtras ex = {};
@@ -174,13 +198,19 @@ extern "C" int exl2b_qmlp_create(const exl2b_qmlp_desc* d, exl2b_qmlp_t* out) {
     EXL2B_REQUIRE(g->v.N == d->intermediate_size && u->v.N == d->intermediate_size && (!dn || dn->v.K == d->intermediate_size),
                   "mlp intermediate size mismatch");
     EXL2B_REQUIRE(g->device == u->device && (!dn || g->device == dn->device), "handles on different devices");
-    QMlp* m = new QMlp{*d, g->device};
+    const QMatrix* gu[2] = {g, u};
+    QMlp* m = new QMlp{*d, g->device, gemv_i8_fusable(gu, 2), nullptr};
     *out = (exl2b_qmlp_t)m;
     return 0;
 }
 
 extern "C" int exl2b_qmlp_destroy(exl2b_qmlp_t h) {
-    delete (QMlp*)h;
+    QMlp* m = (QMlp*)h;
+    if (m && m->up_scratch) {
+        cudaSetDevice(m->device);
+        cudaFree(m->up_scratch);
+    }
+    delete m;
     return 0;
 }
 
@@ -199,6 +229,21 @@ extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint
         make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
     };
     GemvMat down = make_mat(dn, (const half*)temp_a, d.intermediate_size, (half*)x, d.hidden_size, d.has_residual ? 0 : 1);
+    if (rows == 1 && !input_prepared && !(next && next->num_consumers > 0) && m->i8_gu && dn->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
+        // decode row: gate|up in one launch with RMSNorm as its prologue; act(gate) * up is the PROLOGUE of the down launch
+        half* tb = (half*)temp_b;
+        if (!tb) {
+            if (!m->up_scratch) EXL2B_CUDA(cudaMalloc(&m->up_scratch, (size_t)d.intermediate_size * sizeof(half)));
+            tb = m->up_scratch;
+        }
+        const I8Out o[2] = {{g, (half*)temp_a, 1}, {u, tb, 1}};
+        const I8Input in1 = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN};
+        int rc = gemv_i8_launch(m->device, stream, o, 2, in1);
+        if (rc) return rc;
+        const I8Out od = {dn, (half*)x, d.has_residual ? 0 : 1};
+        const I8Input in2 = {(const half*)temp_a, tb, nullptr, 0.f, d.act_gelu ? I8_GELU_MUL : I8_SILU_MUL};
+        return gemv_i8_launch(m->device, stream, &od, 1, in2);
+    }
     const int epi = d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL;
     const bool fuse = gemv_supports_extras(gu, 2, rows) && gemv_supports_extras(&down, 1, rows);
     EXL2B_REQUIRE(fuse || (!input_prepared && !(next && next->num_consumers > 0)),
@@ -277,4 +322,17 @@ extern "C" int exl2b_qmatrix_chain_target(exl2b_qmatrix_t h, uint16_t** xp, cons
     *xp = (uint16_t*)q->xp_buf;
     *invperm = q->invperm;
     return 0;
+}
+
+// rms_norm + gemm_half_q_half on ONE row as a single launch (final norm + lm_head of a decode step; the reference runs
+// rms_norm_cuda then gemm_half_q_half_cuda, exllamav2/model.py:1036-1044 -> rmsnorm.py:141, linear.py:366)
+extern "C" int exl2b_gemm_half_q_half_norm(exl2b_qmatrix_t h, const uint16_t* x, const uint16_t* norm_w, float norm_eps,
+                                           uint16_t* c, int clear, exl2b_stream_t stream) {
+    QMatrix* q = (QMatrix*)h;
+    EXL2B_REQUIRE(q && x && norm_w && c, "null argument");
+    EXL2B_REQUIRE(q->v.layout == LAYOUT_TC, "matrix is not in the default layout");
+    EXL2B_CUDA(cudaSetDevice(q->device));
+    const I8Out o = {q, (half*)c, clear ? 1 : 0};
+    const I8Input in = {(const half*)x, nullptr, (const half*)norm_w, norm_eps, I8_RMSNORM};
+    return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
 }

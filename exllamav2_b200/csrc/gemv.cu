@@ -22,6 +22,7 @@
 
 #include "dequant.cuh"
 #include "gemv.cuh"
+#include "gemv_i8.cuh"
 
 namespace exl2b {
 
@@ -655,6 +656,11 @@ extern "C" int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int 
     EXL2B_REQUIRE(q && a && c, "null argument");
     EXL2B_REQUIRE(lda >= q->v.K && ldc >= q->v.N, "leading dimensions too small");
     EXL2B_CUDA(cudaSetDevice(q->device));
+    if (m == 1 && q->v.layout == LAYOUT_TC && gemv_i8_enabled()) {        // decode row: the HBM-bound integer GEMV (gemv_i8.cu)
+        const I8Out o = {q, (half*)c, clear ? 1 : 0};
+        const I8Input in = {(const half*)a, nullptr, nullptr, 0.f, I8_PLAIN};
+        return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
+    }
     GemvMat mt = {};
     mt.w = q->v;
     mt.x = (const half*)a;

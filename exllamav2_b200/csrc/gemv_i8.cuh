@@ -1,0 +1,39 @@
+// Batch-1 dequant-GEMV on the integer dot-product pipe (gemv_i8.cu): host interface.
+#pragma once
+#include "qmatrix.cuh"
+
+namespace exl2b {
+
+constexpr int I8_MAX_MATS = 3;
+
+// What the kernel's prologue does to the input row before it is quantised to 16-bit integers (all of it in the
+// reference's op order and roundings, so the row the dot products see is the fp16 row the reference's GEMV would read):
+enum I8Mode : int {
+    I8_PLAIN = 0,      // a = x
+    I8_RMSNORM = 1,    // a = half(x * w * rsqrt(mean(x^2) + eps))              rms_norm_kernel, cuda/rms_norm.cu:55-143
+    I8_SILU_MUL = 2,   // a = half(half(silu(x)) * x2)                           act_mul_kernel, cuda/q_mlp_activation.cuh:54-100
+    I8_GELU_MUL = 3,
+};
+
+struct I8Input {
+    const half* x;        // fp16 [K]
+    const half* x2;       // fp16 [K] (I8_*_MUL) or NULL
+    const half* norm_w;   // fp16 [K] (I8_RMSNORM) or NULL
+    float norm_eps;
+    int mode;
+};
+
+struct I8Out {
+    const QMatrix* q;
+    half* c;              // fp16 [N]
+    int clear;            // 1: c = acc (+bias); 0: c += acc (+bias)   (residual add, cuda/q_attn.cu:333)
+};
+
+// One launch over `nm` matrices that share K, the input row and the row permutation.  M = 1 only.
+int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, const I8Input& in);
+// same K / same permutation contents / tcgen05 layout?  (host check, synchronises once; call at block-creation time)
+bool gemv_i8_fusable(const QMatrix* const* qs, int nm);
+// EXL2B_GEMV=tc in the environment routes single rows through the tcgen05 kernel instead (A/B comparisons)
+bool gemv_i8_enabled();
+
+}  // namespace exl2b

@@ -69,6 +69,7 @@ _sig("exl2b_qmatrix_destroy", c_int, c_void_p)
 _sig("exl2b_qmatrix_info", c_int, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_uint64))
 _sig("exl2b_reconstruct", c_int, c_void_p, c_void_p, c_void_p)
 _sig("exl2b_gemm_half_q_half", c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p)
+_sig("exl2b_gemm_half_q_half_norm", c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p)
 _sig("exl2b_gemm_half_q_half_host", c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p)
 _sig("exl2b_make_group_map", c_int, POINTER(c_int16), c_int, c_int, POINTER(c_int16), c_int, POINTER(c_int))
 _sig("exl2b_rms_norm", c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p)
@@ -227,6 +228,24 @@ def gemm_half_q_half(a: torch.Tensor, b: int, c: torch.Tensor, force_cuda: bool 
         raise RuntimeError("a and c must be row-major")
     _check(lib.exl2b_gemm_half_q_half(b, a.data_ptr(), a.stride(0), c.data_ptr(), c.stride(0), a.shape[0], 1,
                                       int(force_cuda), _stream(a)))
+
+
+def gemv_norm(x: torch.Tensor, b: int, w: torch.Tensor, epsilon: float, c: torch.Tensor, clear: bool = True):
+    """rms_norm(x, w) followed by gemm_half_q_half, fused into one launch for a single row (decode: final norm + lm_head);
+    more rows run the two reference ops (rmsnorm.py:141, linear.py:366)."""
+    _cuda(x, "x")
+    _dtype(x, torch.float16, "x")
+    _dtype(c, torch.float16, "c")
+    rows = x.numel() // x.shape[-1]
+    if rows == 1:
+        _check(lib.exl2b_gemm_half_q_half_norm(b, x.data_ptr(), w.data_ptr(), float(epsilon), c.data_ptr(), int(clear), _stream(x)))
+        return
+    y = torch.empty_like(x)
+    rms_norm(x, w, y, epsilon)
+    if clear:
+        gemm_half_q_half(y.view(rows, -1), b, c.view(rows, -1), False)
+    else:
+        gemm_half_q_half_accum(y.view(rows, -1), b, c.view(rows, -1))
 
 
 def gemm_half_q_half_accum(a: torch.Tensor, b: int, c: torch.Tensor):

@@ -142,9 +142,9 @@ class ExLlamaV2Decoder:
         self.linears: list[ExLlamaV2Linear] = []
         max_rows = 64
 
-        def lin(K, N, plan, s):
+        def lin(K, N, plan, s, perm_seed=None):
             bits, prop, gs = plan
-            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K))
+            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
             self.weight_bytes += synthetic.algorithmic_bytes(w, 1)
             l = ExLlamaV2Linear(K, N, device=dev)
             l.load(w)
@@ -155,14 +155,16 @@ class ExLlamaV2Decoder:
         for li in range(cfg.num_layers):
             L = _Layer()
             mp = cfg.plan.mlp[li % len(cfg.plan.mlp)]
-            L.q_proj, L.k_proj = lin(hid, H * hd, cfg.plan.attn, s + 1), lin(hid, KVH * hd, cfg.plan.attn, s + 2)
-            L.v_proj, L.o_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 3), lin(H * hd, hid, cfg.plan.attn, s + 4)
-            L.gate, L.up, L.down = lin(hid, inter, mp, s + 5), lin(hid, inter, mp, s + 6), lin(inter, hid, mp, s + 7)
+            # k / v reuse q's row permutation and up reuses gate's, as the reference's converter produces them
+            # (conversion/quantize.py:138-139,159: reuse_h copies the activation-order permutation)
+            L.q_proj, L.k_proj = lin(hid, H * hd, cfg.plan.attn, s + 1, s + 1), lin(hid, KVH * hd, cfg.plan.attn, s + 2, s + 1)
+            L.v_proj, L.o_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 3, s + 1), lin(H * hd, hid, cfg.plan.attn, s + 4)
+            L.gate, L.up, L.down = lin(hid, inter, mp, s + 5, s + 5), lin(hid, inter, mp, s + 6, s + 5), lin(inter, hid, mp, s + 7)
             s += 16
             L.input_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
             L.post_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
             L.temp_a = torch.empty((max_rows, inter), dtype=torch.half, device=dev)
-            L.temp_b = none_tensor
+            L.temp_b = torch.empty((max_rows, inter), dtype=torch.half, device=dev)
             L.attn = ext_c.make_q_attn(L.input_norm, none_tensor, True, False, cfg.norm_eps, L.q_proj.q_handle, L.k_proj.q_handle,
                                        L.v_proj.q_handle, L.o_proj.q_handle, none_tensor, none_tensor, max_rows, hid, H, KVH, hd,
                                        cfg.max_seq_len, True, 2, hd, none_tensor, none_tensor, none_tensor, none_tensor, False, True)
@@ -193,6 +195,8 @@ class ExLlamaV2Decoder:
         self.fused_attn = os.environ.get("EXL2B_REF_KV_SEQUENCE") is None
         # producer epilogues feed consumer activation buffers (needs the default tcgen05 matrix layout)
         self.chained = os.environ.get("EXL2B_NO_CHAIN") is None and not os.environ.get("EXL2B_LAYOUT", "").startswith("m")
+        # single rows (bs = 1 decode) run on the HBM-bound integer GEMV (csrc/gemv_i8.cu) in the reference's own op sequence
+        self.row_gemv = os.environ.get("EXL2B_GEMV", "")[:1] != "t"
         for L in self.layers:
             L.chain_attn = ext_c.make_chain([L.q_proj.q_handle, L.k_proj.q_handle, L.v_proj.q_handle], L.input_norm)
             L.chain_mlp = ext_c.make_chain([L.gate.q_handle, L.up.q_handle], L.post_norm)
@@ -204,7 +208,7 @@ class ExLlamaV2Decoder:
         B = self.batch_size
         stream = torch.cuda.current_stream(self.device).cuda_stream
         H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
-        if self.chained and self.fused_attn and B * q_len <= 8:
+        if self.chained and self.fused_attn and B * q_len <= 8 and not (self.row_gemv and B * q_len == 1):
             return self._forward_tokens_chained(x, q, k, v, attn_out, q_len)
         for li, L in enumerate(self.layers):
             if self.fused_attn and q_len <= 8:
@@ -256,6 +260,10 @@ class ExLlamaV2Decoder:
 
     def _decode_step(self):
         torch.index_select(self.embed, 0, self.ids.view(-1), out=self.x.view(self.batch_size, -1))
+        if self.row_gemv and self.batch_size == 1:
+            self._forward_tokens(self.x, self.q, self.k, self.v, self.attn_out, 1)
+            ext_c.gemv_norm(self.x.view(1, -1), self.lm_head.q_handle, self.final_norm, self.cfg.norm_eps, self.logits)
+            return
         if self.chained and self.fused_attn and self.batch_size <= 8:
             self._forward_tokens_chained(self.x, self.q, self.k, self.v, self.attn_out, 1, head=True)
             ext_c.gemm_half_q_half_prepared(self.lm_head.q_handle, self.logits, True, self.cfg.norm_eps)

@@ -32,7 +32,7 @@ def group_plan(K: int, bits, bits_prop, group_size) -> list[tuple[int, int]]:
 
 
 def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, device="cuda:0", seed: int = 0,
-                perm: bool = True, weight_std: float | None = None) -> dict:
+                perm: bool = True, weight_std: float | None = None, perm_seed: int | None = None) -> dict:
     """Random EXL2 tensors.  weight_std: nominal standard deviation of the dequantised weights -- the realised one is
     ~1.4x larger because scale nibbles are uniform, see tests/test_synthetic.py -- (1/sqrt(K) keeps a
     random-init network's activations O(1), like a trained checkpoint's ~0.02 at K = 4096); None: scale_max in
@@ -54,6 +54,11 @@ def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, dev
         "q_groups": q_groups.to(device),
         "q_invperm": (torch.randperm(K, device=device, generator=gen) if perm else torch.arange(K, device=device)).to(torch.int32),
     }
+    if perm and perm_seed is not None:
+        # matrices quantised against the same input share one activation-order permutation (conversion/quantize.py:138-139)
+        pg = torch.Generator(device=device)
+        pg.manual_seed(0x5EED0000 + perm_seed)
+        w["q_invperm"] = torch.randperm(K, device=device, generator=pg).to(torch.int32)
     if weight_std is not None:
         # std of (q - 2^(b-1)) for uniform q is 2^b / sqrt(12); E[(s+1)^2] for a uniform 4-bit scale nibble is 93.5;
         # the stored q_scale_max carries a factor 256 (the loader multiplies by 1/256, ext.py:336 of the reference)

@@ -76,6 +76,12 @@ int exl2b_reconstruct(exl2b_qmatrix_t h, uint16_t* out, exl2b_stream_t stream);
 int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int lda, uint16_t* c, int ldc, int m, int clear,
                            int force_cuda, exl2b_stream_t stream);
 
+/* rms_norm (ext_norm.cpp:23-62) + gemm_half_q_half on ONE row as a single launch -- the final norm + lm_head of a decode
+ * step (exllamav2/model.py:1036-1044 runs them as two kernels): c[n] = (clear ? 0 : c[n]) + bias[n] +
+ * sum_k half(x[k] * w[k] * rsqrt(mean(x^2) + eps)) * W[k, n];  x fp16[K], c fp16[N]. */
+int exl2b_gemm_half_q_half_norm(exl2b_qmatrix_t h, const uint16_t* x, const uint16_t* norm_w, float norm_eps, uint16_t* c,
+                                int clear, exl2b_stream_t stream);
+
 /* make_group_map (ext_qmatrix.cpp:341-361): host-only helper, out int16[2*K]; returns rows written / 2 in *k. */
 int exl2b_make_group_map(const int16_t* q_groups, int num_groups, int num_qrows, int16_t* out, int out_capacity, int* k);
 

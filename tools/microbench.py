@@ -127,6 +127,7 @@ def main():
                     for i in range(nl):
                         r = st[i]
                         print(json.dumps({"shape": name, "M": M, "cta": cta, "launch": i, "grid_start": r[6] - t0, "grid_end": r[7] - t0,
+                                          "rel_to_grid_start[start,requested,wait_done,staged,warp0_done,all_warps_done]": [x - r[6] for x in r[:6]], "grid_ns": r[7] - r[6],
                                           "cta[start,prefetched,wait_done,staged,consumed,done]": [x - t0 for x in r[:6]],
                                           "clk[w0|w1|w4: waits(weights+A_free),unpack,drain:wait_D,drain:rest ; w8(issue): waits(act+A_full),S+arrive,MMAs,commits]": [r[8:12], r[12:16], r[16:20], r[20:24]]}), flush=True)
             t_eager = time_loop(run_new, 5)
@@ -151,6 +152,18 @@ def main():
                         run_ref()
                 t_ref = time_loop(run_ref, 5)
                 row.update(ref_us=t_ref * 1e3 / n, ref_gbs=per_call * n / t_ref / 1e6)
+                # the same calls replayed from a CUDA graph: the reference without its host launch overhead
+                try:
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(stream):
+                        run_ref()
+                        torch.cuda.synchronize()
+                        with torch.cuda.graph(gr, stream=stream):
+                            run_ref()
+                    t_refg = time_loop(gr.replay, 10)
+                    row.update(ref_graph_us=t_refg * 1e3 / n, ref_graph_gbs=per_call * n / t_refg / 1e6)
+                except Exception as ex:      # noqa: BLE001
+                    row.update(ref_graph_error=str(ex)[:200])
             print(json.dumps(row), flush=True)
             results.append(row)
         for h in handles:
