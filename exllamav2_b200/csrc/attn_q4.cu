@@ -14,6 +14,7 @@
 //     them attends them UNQUANTISED (fp16 values, rotated in fp32), exactly like the reference, where
 //     flash_attn_with_kvcache sees the fp16 rows and the cache only quantises them afterwards (attn.py:602-621).
 // One CTA per (head, sequence); decode regime (q_len <= 8).
+#include "gemv_i8.cuh"
 #include "qmatrix.cuh"
 
 namespace exl2b {
@@ -37,7 +38,47 @@ struct AttnQ4Params {
     const uint16_t* out_invperm;
     int q_len, H, KVH, hd, page_size, pages_per_seq, max_ctx;
     float scale_log2;       // softmax_scale * log2(e)
+    // optional fused RoPE: q and k_new arrive UN-rotated (straight from the Q|K|V projection) and are rotated as they are read,
+    // with the fp16 op order of rope_kernel / cuda/rope.cu:52-67,111-122; position of row i = cache_seqlens[b] + i
+    const half* rope_sin;   // [max_pos, sincos_size] or NULL
+    const half* rope_cos;
+    int rope_neox, sincos_size;
+    int out_plain;          // out_xp is a plain fp16 row (single-row GEMV consumer) instead of the UMMA operand layout
+    int32_t* err;           // sticky device flag: bit 0 = a sequence ran past its page table (nothing appended, no output)
 };
+
+// one half2 (elements un*64 + 2*lane, +1) of a head row, rotated if RoPE is fused.  Warp-uniform call.
+template <int HD>
+__device__ __forceinline__ half2 load_roped(const half* __restrict__ row, int un, int lane, const AttnQ4Params& P, int pos) {
+    const half2 v = reinterpret_cast<const half2*>(row + un * 64)[lane];
+    if (!P.rope_sin) return v;
+    const half* sr = P.rope_sin + (size_t)pos * P.sincos_size;
+    const half* cr = P.rope_cos + (size_t)pos * P.sincos_size;
+    if (P.rope_neox) {
+        half2 o;
+        int col;
+        bool first;
+        if constexpr (HD == 128) {            // partner element j + 64 lives in the other 64-value unit, same lane
+            o = reinterpret_cast<const half2*>(row + (un ^ 1) * 64)[lane];
+            col = 2 * lane;
+            first = (un == 0);
+        } else {                              // HD == 64: partner j + 32 is lane ^ 16
+            o = __shfl_xor_sync(0xffffffffu, v, 16);
+            col = 2 * (lane & 15);
+            first = lane < 16;
+        }
+        const half2 c2 = *reinterpret_cast<const half2*>(cr + col);
+        const half2 s2 = *reinterpret_cast<const half2*>(sr + col);
+        if (first) return __hfma2(v, c2, __hmul2(o, __hneg2(s2)));      // l' = l c + half(r * -s)
+        return __hfma2(v, c2, __hmul2(o, s2));                            // r' = r c + half(l * s)
+    }
+    const int col = un * 64 + 2 * lane;
+    const half2 c01 = *reinterpret_cast<const half2*>(cr + col);
+    half2 s01 = *reinterpret_cast<const half2*>(sr + col);
+    uint32_t sb = *reinterpret_cast<uint32_t*>(&s01) ^ (1u << 15);        // (-sin[i], +sin[i+1])
+    s01 = *reinterpret_cast<half2*>(&sb);
+    return __hfma2(__lowhigh2highlow(v), s01, __hmul2(v, c01));
+}
 
 // fp32 Hadamard-32 across the warp on both halves of a float2 (same butterfly as cache_q.cuh, exact sign handling)
 __device__ __forceinline__ float2 hadamard32_f(float2 w, int lane) {
@@ -92,6 +133,10 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     //      kernel in front of us in the stream, the Q|K|V projection, writes none of it).  The first cached K row of every
     //      thread and the first 16 cached V rows of every warp are already in registers when q / k_new / v_new arrive.
     const int seqlen = P.cache_seqlens[b];
+    if (seqlen < 0 || seqlen + P.q_len > P.max_ctx) {      // the page table / score buffer end here: refuse instead of corrupting
+        if (tid == 0 && P.err) atomicOr(P.err, 1);
+        return;
+    }
     const int32_t* btg = P.block_table + (size_t)b * P.pages_per_seq;
     constexpr int PV_UNROLL = 8;
     uint4 kpre[NSC];                   // the cached K row this thread currently holds (position k_held)
@@ -127,7 +172,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     // ---- 1. quantise the new rows (fp16_to_q_kv arithmetic) on the first warps, keep them in shared memory; at the same
     //      time the LAST warps rotate the first query: qrot = H q * (softmax_scale * log2 e / 32)
     auto rotate_q = [&](int i, int un) {
-        const half2 qh = reinterpret_cast<const half2*>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD + un * 64)[lane];
+        const half2 qh = load_roped<HD>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD, un, lane, P, seqlen + i);
         float2 w = hadamard32_f(__half22float2(qh), lane);
         const float f = P.scale_log2 * (1.0f / 32.0f);
         qrot[un * 64 + 2 * lane] = w.x * f;
@@ -138,8 +183,8 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     for (int job = (warp >= AQ_WARPS - UNITS && n_jobs <= AQ_WARPS - UNITS) ? n_jobs : warp; job < n_jobs; job += AQ_WARPS) {
         const int kv = job / (P.q_len * UNITS), r = job - kv * P.q_len * UNITS;
         const int i = r / UNITS, un = r - i * UNITS;
-        const half* src = (kv ? P.v_new : P.k_new) + (((size_t)b * P.q_len + i) * P.KVH + kvh) * HD + un * 64;
-        half2 w2 = reinterpret_cast<const half2*>(src)[lane];
+        const half* src = (kv ? P.v_new : P.k_new) + (((size_t)b * P.q_len + i) * P.KVH + kvh) * HD;
+        half2 w2 = kv ? reinterpret_cast<const half2*>(src + un * 64)[lane] : load_roped<HD>(src, un, lane, P, seqlen + i);
         {
             const float2 y = hadamard32_f(__half22float2(w2), lane);
             new_y[(kv * AQ_MAX_QLEN + i) * HD + un * 64 + 2 * lane] = y.x;
@@ -334,8 +379,13 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
             if (P.out_xp) {
                 const int n = h * HD + warp * 64 + 2 * lane, m = b * P.q_len + i;
                 const int k0 = P.out_invperm ? (int)P.out_invperm[n] : n, k1 = P.out_invperm ? (int)P.out_invperm[n + 1] : n + 1;
-                P.out_xp[(size_t)(k0 >> 3) * 64 + m * 8 + (k0 & 7)] = __low2half(o2);
-                P.out_xp[(size_t)(k1 >> 3) * 64 + m * 8 + (k1 & 7)] = __high2half(o2);
+                if (P.out_plain) {
+                    P.out_xp[k0] = __low2half(o2);
+                    P.out_xp[k1] = __high2half(o2);
+                } else {
+                    P.out_xp[(size_t)(k0 >> 3) * 64 + m * 8 + (k0 & 7)] = __low2half(o2);
+                    P.out_xp[(size_t)(k1 >> 3) * 64 + m * 8 + (k1 & 7)] = __high2half(o2);
+                }
             }
         }
         __syncthreads();
@@ -346,11 +396,33 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 
 using namespace exl2b;
 
+static int32_t* g_attn_err[64] = {nullptr};
+
+extern "C" int exl2b_paged_attn_status(int device, int* status) {
+    EXL2B_REQUIRE(status && device >= 0 && device < 64, "bad argument");
+    *status = 0;
+    if (!g_attn_err[device]) return 0;
+    EXL2B_CUDA(cudaSetDevice(device));
+    EXL2B_CUDA(cudaMemcpy(status, g_attn_err[device], sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int exl2b_paged_attn_decode_q4(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint8_t* k_cache,
                                           uint16_t* k_scales, uint8_t* v_cache, uint16_t* v_scales, const int32_t* cache_seqlens,
                                           const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
                                           int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
                                           exl2b_qmatrix_t out_consumer, exl2b_stream_t stream) {
+    return exl2b_paged_attn_decode_q4_ex(q, k_new, v_new, k_cache, k_scales, v_cache, v_scales, cache_seqlens, block_table, out, batch,
+                                         q_len, num_heads, num_kv_heads, head_dim, page_size, pages_per_seq, softmax_scale, out_consumer,
+                                         nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint8_t* k_cache,
+                                             uint16_t* k_scales, uint8_t* v_cache, uint16_t* v_scales, const int32_t* cache_seqlens,
+                                             const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
+                                             int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
+                                             exl2b_qmatrix_t out_consumer, const uint16_t* rope_sin, const uint16_t* rope_cos,
+                                             int rope_style, int sincos_size, exl2b_stream_t stream) {
     EXL2B_REQUIRE(q && k_new && v_new && k_cache && k_scales && v_cache && v_scales && cache_seqlens && block_table && out, "null argument");
     EXL2B_REQUIRE(head_dim == 64 || head_dim == 128, "head_dim %d not supported (64 or 128)", head_dim);
     EXL2B_REQUIRE(num_heads % num_kv_heads == 0, "bad GQA ratio");
@@ -371,14 +443,29 @@ extern "C" int exl2b_paged_attn_decode_q4(const uint16_t* q, const uint16_t* k_n
         if (rc) return rc;
         P.out_xp = oc->xp_buf;
         P.out_invperm = oc->invperm;
+        P.out_plain = (batch * q_len == 1 && gemv_i8_enabled()) ? 1 : 0;      // the single-row GEMV reads a plain fp16 row
+    }
+    if (rope_style != 0 && rope_sin && rope_cos) {
+        EXL2B_REQUIRE(sincos_size == head_dim, "fused RoPE needs sincos_size == head_dim (partial rotary: apply rope_ first)");
+        P.rope_sin = (const half*)rope_sin;
+        P.rope_cos = (const half*)rope_cos;
+        P.rope_neox = rope_style == 2;
+        P.sincos_size = sincos_size;
+    }
+    int dev = 0;
+    EXL2B_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64) {
+        if (!g_attn_err[dev]) {
+            EXL2B_CUDA(cudaMalloc(&g_attn_err[dev], sizeof(int32_t)));
+            EXL2B_CUDA(cudaMemset(g_attn_err[dev], 0, sizeof(int32_t)));
+        }
+        P.err = g_attn_err[dev];
     }
     const int hd = head_dim;
     const size_t smem = (size_t)(hd + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
                         (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)(P.max_ctx + q_len) * 4;
     EXL2B_REQUIRE(smem <= 200 * 1024, "context of %d tokens does not fit the score buffer", P.max_ctx);
     static bool attr_set[64] = {false};
-    int dev = 0;
-    EXL2B_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev]) {
         EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -67,6 +67,19 @@ static int chain_in(GemvExtras& ex, GemvMat* mats, const QMatrix* const* qs, int
     return 0;
 }
 
+// i8 (single-row) form of a chain: the producer's finalisation scatters a second fp16 copy of its output into the first
+// consumer's row buffer, in that matrix's stored-row order (all consumers of one chain share their permutation)
+static int chain_out_i8(I8Out& o, const exl2b_chain_t* next, int slot = 0) {
+    if (!next || next->num_consumers <= 0) return 0;
+    QMatrix* c = (QMatrix*)next->consumers[0];
+    EXL2B_REQUIRE(c && c->v.layout == LAYOUT_TC, "chained consumer must be a default-layout matrix");
+    int rc = qmatrix_chain_buffers(c);
+    if (rc) return rc;
+    o.c_perm = c->xp_buf + (size_t)slot * c->v.K;
+    o.out_invperm = c->invperm;
+    return 0;
+}
+
 }  // namespace exl2b
 
 using namespace exl2b;
@@ -110,14 +123,19 @@ extern "C" int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int 
         make_mat(mv, (const half*)x, d.hidden_size, (half*)v, mv->v.N, 1),
     };
     const bool rope = d.rope_style != 0;
-    if (rope) EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
-    if (rows == 1 && !input_prepared && a->i8_qkv && gemv_i8_enabled()) {
-        // decode row: RMSNorm is the GEMV's prologue, Q|K|V are one launch (gemv_i8.cu); RoPE as in the reference
-        // (q_attn.cu:271-300) -- model.py's decode step instead lets the attention kernel rotate q / k as it reads them
+    if (rows == 1 && a->i8_qkv && gemv_i8_enabled()) {
+        // decode row: RMSNorm is the GEMV's prologue, Q|K|V are one launch (gemv_i8.cu).  input_prepared: the row was left in
+        // q_proj's stored-row order by the producer launch (I8Out::c_perm -> q_proj's row buffer).  RoPE as in the reference
+        // (q_attn.cu:271-300) unless the caller passes no tables: exl2b_paged_attn_decode_q4_ex rotates q / k as it reads them.
         const I8Out o[3] = {{mq, (half*)q, 1}, {mk, (half*)k, 1}, {mv, (half*)v, 1}};
-        const I8Input in = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN};
+        I8Input in = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN, 0};
+        if (input_prepared) {
+            EXL2B_REQUIRE(mq->xp_buf, "input_prepared set, but no chained producer has written q_proj's input row");
+            in.x = mq->xp_buf;
+            in.x_permuted = 1;
+        }
         int rc = gemv_i8_launch(a->device, stream, o, 3, in);
-        if (rc || !rope || past_len == -2) return rc;          // past_len == -2: caller applies RoPE itself (fused attention)
+        if (rc || !rope || !sin) return rc;
         const int neox = d.rope_style == 2;
         rc = rope_launch(stream, (half*)q, (const half*)sin, (const half*)cos, batch, q_len * d.num_heads, d.head_dim, d.num_heads,
                          past_len, past_lens, neox, d.sincos_size);
@@ -125,6 +143,7 @@ extern "C" int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int 
         return rope_launch(stream, (half*)k, (const half*)sin, (const half*)cos, batch, q_len * d.num_kv_heads, d.head_dim,
                            d.num_kv_heads, past_len, past_lens, neox, d.sincos_size);
     }
+    if (rope) EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
     const bool fuse = gemv_supports_extras(mats, 3, rows) && (!rope || (d.head_dim <= 128 && 128 % d.head_dim == 0 && d.sincos_size <= d.head_dim));
     EXL2B_REQUIRE(!input_prepared || fuse, "input_prepared needs the tcgen05 layout and at most %d rows", GEMV_MTOK);
     if (fuse) {
@@ -166,9 +185,16 @@ extern "C" int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint
     const QMatrix* mo = (const QMatrix*)a->d.o_proj;
     GemvMat m = make_mat(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, a->d.has_residual ? 0 : 1);
     const bool want = input_prepared || (next && next->num_consumers > 0);
-    if (!want && batch * q_len == 1 && mo->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
-        const I8Out o = {mo, (half*)x, a->d.has_residual ? 0 : 1};
-        const I8Input in = {(const half*)attn_out, nullptr, nullptr, 0.f, I8_PLAIN};
+    if (batch * q_len == 1 && mo->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
+        I8Out o = {mo, (half*)x, a->d.has_residual ? 0 : 1};
+        I8Input in = {(const half*)attn_out, nullptr, nullptr, 0.f, I8_PLAIN, 0};
+        if (input_prepared) {
+            EXL2B_REQUIRE(mo->xp_buf, "input_prepared set, but no chained producer has written o_proj's input row");
+            in.x = mo->xp_buf;
+            in.x_permuted = 1;
+        }
+        int rc = chain_out_i8(o, next);
+        if (rc) return rc;
         return gemv_i8_launch(a->device, (cudaStream_t)stream, &o, 1, in);
     }
     if (!want) return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
@@ -229,19 +255,32 @@ extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint
         make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
     };
     GemvMat down = make_mat(dn, (const half*)temp_a, d.intermediate_size, (half*)x, d.hidden_size, d.has_residual ? 0 : 1);
-    if (rows == 1 && !input_prepared && !(next && next->num_consumers > 0) && m->i8_gu && dn->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
-        // decode row: gate|up in one launch with RMSNorm as its prologue; act(gate) * up is the PROLOGUE of the down launch
+    if (rows == 1 && m->i8_gu && dn->v.layout == LAYOUT_TC && gemv_i8_enabled()) {
+        // decode row: gate|up in one launch with RMSNorm as its prologue; act(gate) * up is the PROLOGUE of the down launch,
+        // which reads both rows in its own stored-row order (scattered there by the gate|up launch's finalisation)
         half* tb = (half*)temp_b;
         if (!tb) {
             if (!m->up_scratch) EXL2B_CUDA(cudaMalloc(&m->up_scratch, (size_t)d.intermediate_size * sizeof(half)));
             tb = m->up_scratch;
         }
-        const I8Out o[2] = {{g, (half*)temp_a, 1}, {u, tb, 1}};
-        const I8Input in1 = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN};
-        int rc = gemv_i8_launch(m->device, stream, o, 2, in1);
+        int rc = qmatrix_chain_buffers(const_cast<QMatrix*>(dn));
         if (rc) return rc;
-        const I8Out od = {dn, (half*)x, d.has_residual ? 0 : 1};
-        const I8Input in2 = {(const half*)temp_a, tb, nullptr, 0.f, d.act_gelu ? I8_GELU_MUL : I8_SILU_MUL};
+        I8Out o[2] = {{g, (half*)temp_a, 1}, {u, tb, 1}};
+        o[0].c_perm = dn->xp_buf;
+        o[1].c_perm = dn->xp_buf + dn->v.K;
+        o[0].out_invperm = o[1].out_invperm = dn->invperm;
+        I8Input in1 = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN, 0};
+        if (input_prepared) {
+            EXL2B_REQUIRE(g->xp_buf, "input_prepared set, but no chained producer has written gate_proj's input row");
+            in1.x = g->xp_buf;
+            in1.x_permuted = 1;
+        }
+        rc = gemv_i8_launch(m->device, stream, o, 2, in1);
+        if (rc) return rc;
+        I8Out od = {dn, (half*)x, d.has_residual ? 0 : 1};
+        rc = chain_out_i8(od, next);
+        if (rc) return rc;
+        const I8Input in2 = {dn->xp_buf, dn->xp_buf + dn->v.K, nullptr, 0.f, d.act_gelu ? I8_GELU_MUL : I8_SILU_MUL, 1};
         return gemv_i8_launch(m->device, stream, &od, 1, in2);
     }
     const int epi = d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL;
@@ -325,14 +364,20 @@ extern "C" int exl2b_qmatrix_chain_target(exl2b_qmatrix_t h, uint16_t** xp, cons
 }
 
 // rms_norm + gemm_half_q_half on ONE row as a single launch (final norm + lm_head of a decode step; the reference runs
-// rms_norm_cuda then gemm_half_q_half_cuda, exllamav2/model.py:1036-1044 -> rmsnorm.py:141, linear.py:366)
+// rms_norm_cuda then gemm_half_q_half_cuda, exllamav2/model.py:1036-1044 -> rmsnorm.py:141, linear.py:366).
+// x == NULL: the row was left in this matrix's stored-row order by a chained producer launch.
 extern "C" int exl2b_gemm_half_q_half_norm(exl2b_qmatrix_t h, const uint16_t* x, const uint16_t* norm_w, float norm_eps,
                                            uint16_t* c, int clear, exl2b_stream_t stream) {
     QMatrix* q = (QMatrix*)h;
-    EXL2B_REQUIRE(q && x && norm_w && c, "null argument");
+    EXL2B_REQUIRE(q && norm_w && c, "null argument");
     EXL2B_REQUIRE(q->v.layout == LAYOUT_TC, "matrix is not in the default layout");
     EXL2B_CUDA(cudaSetDevice(q->device));
     const I8Out o = {q, (half*)c, clear ? 1 : 0};
-    const I8Input in = {(const half*)x, nullptr, (const half*)norm_w, norm_eps, I8_RMSNORM};
+    I8Input in = {(const half*)x, nullptr, (const half*)norm_w, norm_eps, I8_RMSNORM, 0};
+    if (!x) {
+        EXL2B_REQUIRE(q->xp_buf, "no input row given and no chained producer has written this matrix's input row");
+        in.x = q->xp_buf;
+        in.x_permuted = 1;
+    }
     return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
 }

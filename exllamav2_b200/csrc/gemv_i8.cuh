@@ -6,27 +6,29 @@ namespace exl2b {
 
 constexpr int I8_MAX_MATS = 3;
 
-// What the kernel's prologue does to the input row before it is quantised to 16-bit integers (all of it in the
-// reference's op order and roundings, so the row the dot products see is the fp16 row the reference's GEMV would read):
+// What the kernel's prologue does to the input row before it is quantised to 16-bit integers:
 enum I8Mode : int {
     I8_PLAIN = 0,      // a = x
-    I8_RMSNORM = 1,    // a = half(x * w * rsqrt(mean(x^2) + eps))              rms_norm_kernel, cuda/rms_norm.cu:55-143
-    I8_SILU_MUL = 2,   // a = half(half(silu(x)) * x2)                           act_mul_kernel, cuda/q_mlp_activation.cuh:54-100
+    I8_RMSNORM = 1,    // a = x * w * rsqrt(mean(x^2) + eps)      rms_norm_kernel, cuda/rms_norm.cu:55-143 (1/rms applied to the fp32 sum)
+    I8_SILU_MUL = 2,   // a = half(half(silu(x)) * x2)             act_mul_kernel, cuda/q_mlp_activation.cuh:54-100 (same fp16 op order)
     I8_GELU_MUL = 3,
 };
 
 struct I8Input {
     const half* x;        // fp16 [K]
     const half* x2;       // fp16 [K] (I8_*_MUL) or NULL
-    const half* norm_w;   // fp16 [K] (I8_RMSNORM) or NULL
+    const half* norm_w;   // fp16 [K] (I8_RMSNORM) or NULL, ORIGINAL feature order
     float norm_eps;
     int mode;
+    int x_permuted;       // x / x2 are already in the matrices' stored-row order (written by a producer launch's c_perm)
 };
 
 struct I8Out {
     const QMatrix* q;
-    half* c;              // fp16 [N]
-    int clear;            // 1: c = acc (+bias); 0: c += acc (+bias)   (residual add, cuda/q_attn.cu:333)
+    half* c;                       // fp16 [N]
+    int clear;                     // 1: c = acc (+bias); 0: c += acc (+bias)   (residual add, cuda/q_attn.cu:333)
+    half* c_perm;                  // optional second copy of the NEW c, scattered to c_perm[out_invperm[n]] -- the row order of
+    const uint16_t* out_invperm;   //   the matrix that consumes it next (then that launch reads it contiguously: x_permuted)
 };
 
 // One launch over `nm` matrices that share K, the input row and the row permutation.  M = 1 only.

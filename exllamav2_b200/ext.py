@@ -89,6 +89,8 @@ _sig("exl2b_qmlp_destroy", c_int, c_void_p)
 _sig("exl2b_qmlp_forward", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p)
 _sig("exl2b_qmlp_forward_gateup", c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p)
 _sig("exl2b_paged_attn_decode_q4", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p]))
+_sig("exl2b_paged_attn_decode_q4_ex", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]))
+_sig("exl2b_paged_attn_status", c_int, c_int, POINTER(c_int))
 
 
 class _Chain(Structure):
@@ -230,7 +232,7 @@ def gemm_half_q_half(a: torch.Tensor, b: int, c: torch.Tensor, force_cuda: bool 
                                       int(force_cuda), _stream(a)))
 
 
-def gemv_norm(x: torch.Tensor, b: int, w: torch.Tensor, epsilon: float, c: torch.Tensor, clear: bool = True):
+def gemv_norm(x: torch.Tensor, b: int, w: torch.Tensor, epsilon: float, c: torch.Tensor, clear: bool = True, prepared: bool = False):
     """rms_norm(x, w) followed by gemm_half_q_half, fused into one launch for a single row (decode: final norm + lm_head);
     more rows run the two reference ops (rmsnorm.py:141, linear.py:366)."""
     _cuda(x, "x")
@@ -238,7 +240,9 @@ def gemv_norm(x: torch.Tensor, b: int, w: torch.Tensor, epsilon: float, c: torch
     _dtype(c, torch.float16, "c")
     rows = x.numel() // x.shape[-1]
     if rows == 1:
-        _check(lib.exl2b_gemm_half_q_half_norm(b, x.data_ptr(), w.data_ptr(), float(epsilon), c.data_ptr(), int(clear), _stream(x)))
+        # prepared: the row was left in the matrix's stored-row order by a chained producer launch (exl2b_chain_t)
+        _check(lib.exl2b_gemm_half_q_half_norm(b, None if prepared else x.data_ptr(), w.data_ptr(), float(epsilon), c.data_ptr(),
+                                               int(clear), _stream(x)))
         return
     y = torch.empty_like(x)
     rms_norm(x, w, y, epsilon)
@@ -504,7 +508,7 @@ def gemm_half_q_half_prepared(b: int, c, has_norm: bool, norm_eps: float, clear:
 
 
 def paged_attn_decode_q4(q, k_new, v_new, k_cache, k_scales, v_cache, v_scales, cache_seqlens, block_table, out,
-                         softmax_scale: float, out_consumer: int = 0):
+                         softmax_scale: float, out_consumer: int = 0, rope=None):
     """Decode attention over the paged Q4 cache with quantise-and-append of the new rows (include/exl2_b200.h
     exl2b_paged_attn_decode_q4).  q [B, q_len, H, hd]; k_new / v_new [B, q_len, KVH, hd]; caches uint8
     [pages, page, KVH, hd/2] + fp16 scales [pages, page, KVH, hd/32]; out like q.  No reference counterpart as one op:
@@ -513,10 +517,20 @@ def paged_attn_decode_q4(q, k_new, v_new, k_cache, k_scales, v_cache, v_scales, 
     KVH = k_new.shape[2]
     for t in (q, k_new, v_new, out):
         _dtype(_cuda(t, "attention operand"), torch.half, "attention operand")
-    _check(lib.exl2b_paged_attn_decode_q4(
+    # rope = (sin, cos, rope_style): q / k_new are the un-rotated projection outputs, rotated as the kernel reads them
+    sin, cos, style = rope if rope is not None else (None, None, 0)
+    _check(lib.exl2b_paged_attn_decode_q4_ex(
         _p(q), _p(k_new), _p(v_new), _p(k_cache), _p(k_scales), _p(v_cache), _p(v_scales),
         _p(cache_seqlens), _p(block_table), _p(out), B, q_len, H, KVH, hd, k_cache.shape[1], block_table.shape[1],
-        float(softmax_scale), out_consumer or None, _stream(q)))
+        float(softmax_scale), out_consumer or None, _p(sin), _p(cos), int(style), sin.shape[-1] if sin is not None else 0,
+        _stream(q)))
+
+
+def paged_attn_status(device) -> int:
+    """Sticky error bits of the fused attention kernels (bit 0: a sequence ran past its page table).  Synchronises."""
+    st = c_int(0)
+    _check(lib.exl2b_paged_attn_status(torch.device(device).index or 0, ctypes.byref(st)))
+    return st.value
 
 
 HOT_PATH_EXPORTS = [
@@ -525,6 +539,36 @@ HOT_PATH_EXPORTS = [
     "make_q_attn", "free_q_attn", "q_attn_forward_1", "q_attn_forward_2",
     "make_q_mlp", "free_q_mlp", "q_mlp_forward_",
 ]
+
+
+# Names of the reference extension that are NOT on the hot path (sampling, safetensors loader, MoE, LoRA, head / layer norm,
+# FP8 cache, converter kernels, the single-process TP glue -- SURVEY.md 2.2) are forwarded to the stock extension when the
+# deployment registers one; otherwise the AttributeError says exactly which name is missing and why.
+_stock_ext = None
+
+
+def set_stock_extension(module) -> None:
+    """Register the reference's own build of `exllamav2_ext` (or any module exporting its names) as the provider of
+    everything outside the hot path."""
+    global _stock_ext
+    _stock_ext = module
+
+
+def __getattr__(name: str):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    stock = _stock_ext
+    if stock is None:
+        try:
+            import importlib
+            stock = importlib.import_module("exllamav2_ext_stock")      # a deployment may put the stock build on sys.path under this name
+            set_stock_extension(stock)
+        except ImportError:
+            stock = None
+    if stock is not None and hasattr(stock, name):
+        return getattr(stock, name)
+    raise AttributeError(f"exllamav2_b200.ext: '{name}' is outside the quantized-linear hot path this module replaces and no stock "
+                         f"exllamav2_ext is registered (exllamav2_b200.ext.set_stock_extension / module 'exllamav2_ext_stock')")
 
 
 def install_as_exllamav2_ext():

@@ -208,7 +208,7 @@ class ExLlamaV2Decoder:
         B = self.batch_size
         stream = torch.cuda.current_stream(self.device).cuda_stream
         H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
-        if self.chained and self.fused_attn and B * q_len <= 8 and not (self.row_gemv and B * q_len == 1):
+        if self.chained and self.fused_attn and B * q_len <= 8:
             return self._forward_tokens_chained(x, q, k, v, attn_out, q_len)
         for li, L in enumerate(self.layers):
             if self.fused_attn and q_len <= 8:
@@ -242,13 +242,17 @@ class ExLlamaV2Decoder:
         B = self.batch_size
         H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
         n = len(self.layers)
+        # single rows (the batch-1 integer GEMV): RoPE is left to the attention kernel, which rotates q / k as it reads them
+        fuse_rope = self.row_gemv and B * q_len == 1
         for li, L in enumerate(self.layers):
-            ext_c.q_attn_forward_1_ex(L.attn, x, B, q_len, -1, cache.cache_seqlens, q, k, v, self.sin, self.cos, li > 0)
+            ext_c.q_attn_forward_1_ex(L.attn, x, B, q_len, -1, cache.cache_seqlens, q, k, v,
+                                      None if fuse_rope else self.sin, None if fuse_rope else self.cos, li > 0)
             if not gemv_only:        # (bench.py's roofline loop replays exactly the GEMV launches, nothing else)
                 ext_c.paged_attn_decode_q4(q.view(B, q_len, H, hd), k.view(B, q_len, KVH, hd), v.view(B, q_len, KVH, hd),
                                            cache.key_states[li], cache.key_scales[li], cache.value_states[li],
                                            cache.value_scales[li], cache.cache_seqlens, cache.block_table,
-                                           attn_out.view(B, q_len, H, hd), 1.0 / math.sqrt(hd), L.o_proj.q_handle)
+                                           attn_out.view(B, q_len, H, hd), 1.0 / math.sqrt(hd), L.o_proj.q_handle,
+                                           rope=(self.sin, self.cos, 2) if fuse_rope else None)
             ext_c.q_attn_forward_2_ex(L.attn, x, attn_out, B, q_len, True, L.chain_mlp)
             if li + 1 < n:
                 nxt = self.layers[li + 1].chain_attn
@@ -260,9 +264,9 @@ class ExLlamaV2Decoder:
 
     def _decode_step(self):
         torch.index_select(self.embed, 0, self.ids.view(-1), out=self.x.view(self.batch_size, -1))
-        if self.row_gemv and self.batch_size == 1:
-            self._forward_tokens(self.x, self.q, self.k, self.v, self.attn_out, 1)
-            ext_c.gemv_norm(self.x.view(1, -1), self.lm_head.q_handle, self.final_norm, self.cfg.norm_eps, self.logits)
+        if self.row_gemv and self.batch_size == 1 and self.chained and self.fused_attn:
+            self._forward_tokens_chained(self.x, self.q, self.k, self.v, self.attn_out, 1, head=True)
+            ext_c.gemv_norm(self.x.view(1, -1), self.lm_head.q_handle, self.final_norm, self.cfg.norm_eps, self.logits, prepared=True)
             return
         if self.chained and self.fused_attn and self.batch_size <= 8:
             self._forward_tokens_chained(self.x, self.q, self.k, self.v, self.attn_out, 1, head=True)

@@ -165,6 +165,10 @@ int exl2b_gemm_half_q_half_host(exl2b_qmatrix_t h, const uint16_t* a_host, uint1
  * CTA `cta`, [6] earliest CTA start (pre-fill with ~0), [7] latest CTA end (NULL disables). */
 int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta);
 
+/* Host-only diagnostics (no GPU needed): the 32-column-block -> CTA partition the batch-1 GEMV uses for blocks of the given
+ * byte sizes; out[0..*used] are the block boundaries of the CTAs. */
+int exl2b_debug_partition(const uint32_t* block_bytes, int num_blocks, int ctas, uint16_t* out, int* used);
+
 /* Stand-in for flash_attn_with_kvcache (third-party in the reference, attn.py:602-613): appends the q_len new K/V rows
  * to the paged fp16 cache at [seqlen, seqlen+q_len) and attends causally.  q [batch,q_len,H,hd], k/v_new
  * [batch,q_len,KVH,hd], caches fp16 [pages,page_size,KVH,hd], out [batch,q_len,H,hd]; head_dim 64 or 128. */
@@ -183,6 +187,21 @@ int exl2b_paged_attn_decode_q4(const uint16_t* q, const uint16_t* k_new, const u
                                const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
                                int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
                                exl2b_qmatrix_t out_consumer, exl2b_stream_t stream);
+
+/* Same, with RoPE fused: when rope_style != 0 (1 gptj, 2 neox) and the tables are given, q and k_new are the UN-rotated
+ * projection outputs and are rotated as they are read (rope_cuda arithmetic, cuda/rope.cu:52-67,111-122; position of row i =
+ * cache_seqlens[b] + i), so q_attn_forward_1 can skip its rope launches (pass sin = cos = NULL there).  Needs
+ * sincos_size == head_dim.  With `out_consumer` and a single row the attention output is also left, as a plain fp16 row in
+ * the consumer's stored-row order, where the batch-1 GEMV of o_proj reads it. */
+int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* k_new, const uint16_t* v_new, uint8_t* k_cache,
+                                  uint16_t* k_scales, uint8_t* v_cache, uint16_t* v_scales, const int32_t* cache_seqlens,
+                                  const int32_t* block_table, uint16_t* out, int batch, int q_len, int num_heads,
+                                  int num_kv_heads, int head_dim, int page_size, int pages_per_seq, float softmax_scale,
+                                  exl2b_qmatrix_t out_consumer, const uint16_t* rope_sin, const uint16_t* rope_cos,
+                                  int rope_style, int sincos_size, exl2b_stream_t stream);
+/* Sticky status of the fused attention kernels on `device` (synchronises): bit 0 = a sequence would have run past its page
+ * table (cache_seqlens[b] + q_len > pages_per_seq * page_size); that call appended nothing and wrote no output. */
+int exl2b_paged_attn_status(int device, int* status);
 
 /* ---- chained launches (no reference counterpart; the reference runs norm / projection / rope / activation as separate
  * kernels, q_attn.cu:153-345, q_mlp.cu:78-236).  A producer's epilogue can write its output straight into the

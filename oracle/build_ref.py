@@ -61,6 +61,30 @@ def build(verbose: bool = False) -> str | None:
     return target
 
 
+def build_pypkg() -> str | None:
+    """Byte-compile the reference's PYTHON package (exllamav2/*.py: linear.py, attn.py, mlp.py, cache.py, ext.py, ... -- the
+    callers of the hot path) from the sources where they lie into oracle/_ref/pypkg/exllamav2/ as sourceless .pyc files, so
+    that tests/test_gpu_dropin.py can run the reference's own ExLlamaV2Linear / RMSNorm code on top of OUR extension module
+    on the GPU box (where /root/reference does not exist).  Build output only; nothing is copied into the repository."""
+    import py_compile
+    src = os.path.join(REF_ROOT, "exllamav2")
+    dst = os.path.join(OUT, "pypkg", "exllamav2")
+    stamp = os.path.join(dst, "__init__.pyc")
+    if not os.path.isdir(src):
+        return os.path.dirname(dst) if os.path.exists(stamp) else None
+    if os.path.exists(stamp):
+        return os.path.dirname(dst)
+    for root, dirs, files in os.walk(src):
+        dirs[:] = [d for d in dirs if d not in ("exllamav2_ext", "__pycache__")]
+        rel = os.path.relpath(root, src)
+        for f in files:
+            if f.endswith(".py"):
+                out = os.path.join(dst, rel, f + "c")
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                py_compile.compile(os.path.join(root, f), cfile=out, dfile=os.path.join("exllamav2", rel, f), doraise=True)
+    return os.path.dirname(dst)
+
+
 def load_ref():
     """Import the built reference extension (or return None when it has not been built)."""
     target = os.path.join(OUT, NAME + ".so")
@@ -79,3 +103,4 @@ def load_ref():
 if __name__ == "__main__":
     t = build(verbose="-v" in sys.argv)
     print("reference extension:", t)
+    print("reference python package (byte-compiled):", build_pypkg())

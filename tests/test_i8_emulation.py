@@ -5,8 +5,7 @@ that are pure bookkeeping and that a wrong constant would break silently.
    compose_lane_words), stage a row of 16-bit integers in the order stage_round writes it (high / low byte planes,
    bytes of octet j ordered k = 8j + {0,4,1,5} | {2,6,3,7}) and run the kernel's mask / shift / PRMT selectors; the
    integer sums must equal sum_k a_k q_k exactly.
-2. work split: locate() / CTA ranges / first and last owner of a 64-column pair (split-K workspace slots) for mixed
-   bit widths, several matrices per launch and tiny matrices.
+2. work split: the host-side block -> CTA partition (whole 32-column blocks per CTA, balanced by bytes).
 """
 import numpy as np
 import pytest
@@ -162,91 +161,64 @@ def test_consume_slab_one_hot_every_k():
 
 
 # ---- work split ------------------------------------------------------------------------------------------------------------
+# A CTA owns whole 32-column blocks; the block -> CTA table is computed on the host (gemv_i8.cu i8_partition_blocks) and is
+# reachable without a GPU through the diagnostics hook exl2b_debug_partition.
 
 
-class Mat:
-    def __init__(self, strips, regions, KS):
-        """regions: list of (ks_begin, bits); derives off_base like qmatrix.cu build_regions (TC layout: 128*bits per slab)"""
-        self.strips, self.KS = strips, KS
-        self.reg = []
-        off = 0
-        for i, (ks0, bits) in enumerate(regions):
-            self.reg.append((ks0, bits, off))
-            ks1 = regions[i + 1][0] if i + 1 < len(regions) else KS
-            off += (ks1 - ks0) * 128 * bits
-        self.blk_stream_bytes = off
-        self.pairs = strips * 2
+def _partition(block_bytes, ctas):
+    import ctypes
+
+    from exllamav2_b200 import ext as ext_c
+    f = ext_c.lib.exl2b_debug_partition
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    bb = np.asarray(block_bytes, dtype=np.uint32)
+    out = np.zeros(ctas + 2, dtype=np.uint16)
+    used = ctypes.c_int(0)
+    rc = f(bb.ctypes.data, len(bb), ctas, out.ctypes.data, ctypes.byref(used))
+    assert rc == 0
+    return out[: used.value + 1].astype(int), used.value
 
 
-def locate(mats, KS, pos):
-    mi = 0
-    for i, m in enumerate(mats):
-        if i and pos >= m.byte_base:
-            mi = i
-    m = mats[mi]
-    rel = pos - m.byte_base
-    pair_bytes = 2 * m.blk_stream_bytes
-    p = rel // pair_bytes
-    off = (rel - p * pair_bytes) >> 1
-    r = 0
-    for i, (ks0, bits, ob) in enumerate(m.reg):
-        if i and off >= ob:
-            r = i
-    ks0, bits, ob = m.reg[r]
-    return (m.gp_base + p) * KS + ks0 + (off - ob) // (128 * bits)
+def _best_makespan(block_bytes, ctas):
+    """optimal contiguous partition by dynamic programming (small inputs only)"""
+    n = len(block_bytes)
+    pre = np.concatenate([[0], np.cumsum(block_bytes)])
+    INF = float("inf")
+    dp = [[INF] * (n + 1) for _ in range(ctas + 1)]
+    dp[0][0] = 0
+    for c in range(1, ctas + 1):
+        for j in range(n + 1):
+            dp[c][j] = dp[c - 1][j]
+            for i in range(j):
+                dp[c][j] = min(dp[c][j], max(dp[c - 1][i], pre[j] - pre[i]))
+    return dp[ctas][n]
 
 
-def split(mats, KS, sms=148):
-    bytes_, gp, max_bits = 0, 0, 2
-    for m in mats:
-        m.byte_base, m.gp_base = bytes_, gp
-        gp += m.pairs
-        bytes_ += m.strips * 4 * m.blk_stream_bytes
-        max_bits = max(max_bits, max(b for _, b, _ in m.reg))
-    C = max(1, min(sms, bytes_ // (256 * max_bits)))
-    starts = [locate(mats, KS, bytes_ * c // C) for c in range(C)] + [gp * KS]
-    return bytes_, gp, C, starts
-
-
-def owners(mats, KS, B, C, gp):
-    mi = 0
-    for i, m in enumerate(mats):
-        if i and gp >= m.gp_base:
-            mi = i
-    m = mats[mi]
-    pair_bytes = 2 * m.blk_stream_bytes
-    b0 = m.byte_base + (gp - m.gp_base) * pair_bytes
-    c_first = ((b0 + 256 * m.reg[0][1]) * C - 1) // B
-    c_last = min(C - 1, ((b0 + pair_bytes) * C - 1) // B)
-    return c_first, c_last
-
-
-CASES = [
-    ("4096x4096 [5,4]", [Mat(32, [(0, 5), (16, 4)], 128)], 128),
-    ("qkv fused", [Mat(32, [(0, 5), (16, 4)], 128), Mat(32, [(0, 4)], 128), Mat(32, [(0, 6), (8, 5), (40, 4)], 128)], 128),
-    ("gate|up 4096x11008 [4,3]", [Mat(86, [(0, 4), (16, 3)], 128)] * 1 + [Mat(86, [(0, 4), (16, 3)], 128)], 128),
-    ("down 11008x4096", [Mat(32, [(0, 5), (36, 4)], 344)], 344),
-    ("head 4096x32000 6-bit", [Mat(250, [(0, 6)], 128)], 128),
-    ("tiny 256x128 8-bit", [Mat(1, [(0, 8)], 8)], 8),
-    ("tiny 64x96", [Mat(1, [(0, 4)], 2)], 2),
-    ("K=2048 vocab", [Mat(250, [(0, 6)], 64)], 64),
-    ("2-bit 8192x8192", [Mat(64, [(0, 3), (80, 2)], 256)], 256),
+PART_CASES = [
+    ("qkvo 128 blocks", [65536] * 128, 148),
+    ("qkv fused [5,4] + [4] + [6,5,4]", [67584] * 128 + [65536] * 128 + [70000] * 128, 148),
+    ("gate|up", [60000] * 344 + [60000] * 344, 148),
+    ("head", [98304] * 1000, 148),
+    ("one block", [4096], 148),
+    ("three ragged", [4096, 4096, 2048], 148),
+    ("more ctas than blocks", [1000] * 7, 148),
+    ("few ctas", [10, 20, 30, 40, 50, 60, 70, 80, 90, 100, 5, 5], 4),
 ]
 
 
-@pytest.mark.parametrize("name,mats,KS", CASES, ids=[c[0] for c in CASES])
-def test_work_split(name, mats, KS):
-    B, GP, C, starts = split(mats, KS)
-    assert starts[0] == 0 and all(b > a for a, b in zip(starts, starts[1:])), "every CTA owns at least one unit, in order"
-    for gp in range(GP):
-        lo, hi = gp * KS, (gp + 1) * KS
-        touching = [c for c in range(C) if starts[c] < hi and starts[c + 1] > lo]
-        c_first, c_last = owners(mats, KS, B, C, gp)
-        assert touching == list(range(c_first, c_last + 1)), (name, gp)
-        max_stream = max(m.blk_stream_bytes for m in mats)
-        assert c_last - c_first + 1 <= (2 * max_stream * C) // B + 2
-    # per-CTA row capacity bound used by the launcher
-    max_bits = max(b for m in mats for _, b, _ in m.reg)
-    min_bits = min(b for m in mats for _, b, _ in m.reg)
-    per_cta = (B // C + 256 * max_bits + 256 * min_bits - 1) // (256 * min_bits) + 2
-    assert max(b - a for a, b in zip(starts, starts[1:])) <= per_cta
+@pytest.mark.parametrize("name,bb,ctas", PART_CASES, ids=[c[0] for c in PART_CASES])
+def test_block_partition(name, bb, ctas):
+    bounds, used = _partition(bb, ctas)
+    assert 1 <= used <= ctas
+    assert bounds[0] == 0 and bounds[-1] == len(bb)
+    assert all(b > a for a, b in zip(bounds, bounds[1:])), "every CTA in use owns at least one block, in order"
+    pre = np.concatenate([[0], np.cumsum(bb)])
+    worst = max(pre[b] - pre[a] for a, b in zip(bounds, bounds[1:]))
+    total, biggest = int(pre[-1]), max(bb)
+    assert worst >= max(biggest, -(-total // ctas))
+    if len(bb) <= 16:
+        assert worst == _best_makespan(bb, ctas)
+    else:
+        # uniform-ish blocks: never more than one block above the ideal share
+        assert worst <= -(-total // ctas) + biggest
