@@ -14,6 +14,8 @@
 //     them attends them UNQUANTISED (fp16 values, rotated in fp32), exactly like the reference, where
 //     flash_attn_with_kvcache sees the fp16 rows and the cache only quantises them afterwards (attn.py:602-621).
 // One CTA per (head, sequence); decode regime (q_len <= 8).
+#include <algorithm>
+
 #include "gemv_i8.cuh"
 #include "qmatrix.cuh"
 
@@ -45,7 +47,14 @@ struct AttnQ4Params {
     int rope_neox, sincos_size;
     int out_plain;          // out_xp is a plain fp16 row (single-row GEMV consumer) instead of the UMMA operand layout
     int32_t* err;           // sticky device flag: bit 0 = a sequence ran past its page table (nothing appended, no output)
+    // split-KV (long contexts, q_len == 1): grid.z CTAs share one (head, sequence); each attends a contiguous chunk of positions
+    // and leaves (max, sum, unnormalised rotated output) in `ws`; the last to arrive (counter) merges.  Chunks are at least
+    // AQ_SPLIT_MIN positions, so short contexts use one CTA and never touch the workspace.
+    int nsplit;
+    float* ws;              // [batch][H][nsplit][hd + 2]
+    unsigned int* cnt;      // [batch][H]
 };
+constexpr int AQ_SPLIT_MIN = 512;
 
 // one half2 (elements un*64 + 2*lane, +1) of a head row, rotated if RoPE is fused.  Warp-uniform call.
 template <int HD>
@@ -114,9 +123,10 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     constexpr int VEC = HD / 32;            // values per lane in the dims-on-lanes phase
     constexpr int UNITS = HD / 64;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = P.H / P.KVH, kvh = h / group;
+    __shared__ int s_last;
 
     float* qrot = reinterpret_cast<float*>(smem);                          // [HD]
     float* red = qrot + HD;                                                // [AQ_WARPS][HD]
@@ -138,14 +148,25 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         return;
     }
     const int32_t* btg = P.block_table + (size_t)b * P.pages_per_seq;
+    // this CTA's share of the positions (the whole context unless split-KV is active and the context is long)
+    int ns_act = 1, p_lo = 0, p_hi = seqlen + P.q_len;
+    if (P.nsplit > 1) {
+        const int n_all = seqlen + 1;
+        ns_act = min(P.nsplit, max(1, (n_all + AQ_SPLIT_MIN - 1) / AQ_SPLIT_MIN));
+        if (z >= ns_act) return;
+        const int chunk = (n_all + ns_act - 1) / ns_act;
+        p_lo = z * chunk;
+        p_hi = min(n_all, p_lo + chunk);
+    }
+    const int c_hi = min(p_hi, seqlen);          // cached rows of this CTA: [p_lo, c_hi)
     constexpr int PV_UNROLL = 8;
     uint4 kpre[NSC];                   // the cached K row this thread currently holds (position k_held)
     uint2 kspre = make_uint2(0u, 0u);
     int k_held = -1;
-    if (tid < seqlen) {
-        k_held = tid;
-        const int page = btg[tid / P.page_size];
-        const size_t row = ((size_t)page * P.page_size + tid % P.page_size) * P.KVH + kvh;
+    if (p_lo + tid < c_hi) {
+        k_held = p_lo + tid;
+        const int page = btg[k_held / P.page_size];
+        const size_t row = ((size_t)page * P.page_size + k_held % P.page_size) * P.KVH + kvh;
 #pragma unroll
         for (int blk = 0; blk < NSC; ++blk) kpre[blk] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + blk);
         if constexpr (NSC == 4) kspre = __ldg(reinterpret_cast<const uint2*>(P.k_s + row * NSC));
@@ -154,9 +175,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     uint32_t vpre[PV_UNROLL];          // packed nibbles of my VEC values | fp16 scale << 16
 #pragma unroll
     for (int u = 0; u < PV_UNROLL; ++u) {
-        const int p = warp + u * AQ_WARPS;
+        const int p = p_lo + warp + u * AQ_WARPS;
         vpre[u] = 0x8888u;
-        if (p < seqlen) {
+        if (p < c_hi) {
             const int page = btg[p / P.page_size];
             const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
             uint32_t x;
@@ -206,7 +227,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         if ((lane & 15) == 0) new_s[(kv * AQ_MAX_QLEN + i) * NSC + un * 2 + (lane >> 4)] = __hmul(absmax, __float2half_rn(1.0f / 8.0f));
     }
     __syncthreads();
-    if (h % group == 0) {
+    if (h % group == 0 && z == 0) {
         for (int idx = tid; idx < 2 * P.q_len * (ROWB / 4); idx += AQ_THREADS) {
             const int kv = idx / (P.q_len * (ROWB / 4)), r = idx - kv * P.q_len * (ROWB / 4);
             const int i = r / (ROWB / 4), wd = r - i * (ROWB / 4);
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     };
 
     for (int i = 0; i < P.q_len; ++i) {
-        const int n_ctx = seqlen + i + 1;
+        const int n_ctx = (P.nsplit > 1) ? p_hi : seqlen + i + 1;          // end of the positions this CTA attends for query i
         if (i > 0) {                         // (the first query was rotated above, next to the quantisation)
             if (warp < UNITS) rotate_q(i, warp);
             __syncthreads();
@@ -262,7 +283,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 
         // ---- 2. scores: one position per thread, the whole (rotated) row against qrot ----
         float lmax = -INFINITY;
-        for (int p = tid; p < n_ctx; p += AQ_THREADS) {
+        for (int p = p_lo + tid; p < n_ctx; p += AQ_THREADS) {
             float s;
             if (p >= seqlen) {                   // a row appended by this step: fp16 values, rotated in fp32
                 const float* y = new_y + (p - seqlen) * HD;
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
                 }
                 s = score_row(kpre, kspre);
             }
-            sc[p] = s;
+            sc[p - p_lo] = s;
             lmax = fmaxf(lmax, s);
         }
 #pragma unroll
@@ -298,9 +319,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 #pragma unroll
         for (int w = 1; w < AQ_WARPS; ++w) mx = fmaxf(mx, wred[w]);
         float lsum = 0.f;
-        for (int p = tid; p < n_ctx; p += AQ_THREADS) {
-            const float e = exp2f(sc[p] - mx);
-            sc[p] = e;
+        for (int p = p_lo + tid; p < n_ctx; p += AQ_THREADS) {
+            const float e = exp2f(sc[p - p_lo] - mx);
+            sc[p - p_lo] = e;
             lsum += e;
         }
 #pragma unroll
@@ -329,16 +350,16 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         };
 #pragma unroll
         for (int u = 0; u < PV_UNROLL; ++u) {                                 // rows prefetched before the dependency wait
-            const int p = warp + u * AQ_WARPS;
-            if (p < seqlen) pv_fma(vpre[u], sc[p]);
+            const int p = p_lo + warp + u * AQ_WARPS;
+            if (p < c_hi) pv_fma(vpre[u], sc[p - p_lo]);
         }
-        for (int p0 = warp + PV_UNROLL * AQ_WARPS; p0 < seqlen; p0 += AQ_WARPS * 8) {   // longer contexts: 8 rows in flight
+        for (int p0 = p_lo + warp + PV_UNROLL * AQ_WARPS; p0 < c_hi; p0 += AQ_WARPS * 8) {   // longer contexts: 8 rows in flight
             uint32_t xs[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int p = p0 + u * AQ_WARPS;
                 xs[u] = 0x8888u;
-                if (p < seqlen) {
+                if (p < c_hi) {
                     const int page = bt[p / P.page_size];
                     const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
                     uint32_t x;
@@ -350,12 +371,12 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int p = p0 + u * AQ_WARPS;
-                if (p < seqlen) pv_fma(xs[u], sc[p]);
+                if (p < c_hi) pv_fma(xs[u], sc[p - p_lo]);
             }
         }
         if (warp == 0) {                                                      // rows appended by this step (<= 8)
-            for (int p = seqlen; p < n_ctx; ++p) {
-                const float pe = sc[p];
+            for (int p = max(seqlen, p_lo); p < n_ctx; ++p) {
+                const float pe = sc[p - p_lo];
                 const float* y = new_y + (AQ_MAX_QLEN + p - seqlen) * HD + lane * VEC;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] = fmaf(pe, y[j], acc[j]);
@@ -364,7 +385,62 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < VEC; ++j) red[warp * HD + lane * VEC + j] = acc[j];
         __syncthreads();
-        // ---- 5. sum over warps, rotate back (x = H y / 32), normalise, store ----
+        // ---- 5. sum over warps, (merge the splits,) rotate back (x = H y / 32), normalise, store ----
+        if (ns_act > 1) {
+            // leave (unnormalised rotated output, max, sum) of this chunk; the last CTA of the (head, sequence) merges them all
+            float* wsp = P.ws + (((size_t)b * P.H + h) * P.nsplit + z) * (HD + 2);
+            if (warp < UNITS) {
+                float2 w = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int ww = 0; ww < AQ_WARPS; ++ww) {
+                    w.x += red[ww * HD + warp * 64 + 2 * lane];
+                    w.y += red[ww * HD + warp * 64 + 2 * lane + 1];
+                }
+                __stcg(reinterpret_cast<float2*>(wsp + warp * 64) + lane, w);
+            }
+            if (tid == 0) { __stcg(wsp + HD, mx); __stcg(wsp + HD + 1, denom); }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned old = atomicAdd(P.cnt + (size_t)b * P.H + h, 1u);
+                s_last = (old == (unsigned)ns_act - 1u);
+                if (s_last) P.cnt[(size_t)b * P.H + h] = 0u;
+                __threadfence();
+            }
+            __syncthreads();
+            if (!s_last) return;
+            if (warp < UNITS) {
+                const float* base = P.ws + ((size_t)b * P.H + h) * P.nsplit * (HD + 2);
+                float M = -INFINITY;
+                for (int sidx = 0; sidx < ns_act; ++sidx) M = fmaxf(M, __ldcg(base + (size_t)sidx * (HD + 2) + HD));
+                float2 w = make_float2(0.f, 0.f);
+                float L = 0.f;
+                for (int sidx = 0; sidx < ns_act; ++sidx) {
+                    const float* ps = base + (size_t)sidx * (HD + 2);
+                    const float wgt = exp2f(__ldcg(ps + HD) - M);
+                    const float2 a = __ldcg(reinterpret_cast<const float2*>(ps + warp * 64) + lane);
+                    w.x = fmaf(wgt, a.x, w.x);
+                    w.y = fmaf(wgt, a.y, w.y);
+                    L = fmaf(wgt, __ldcg(ps + HD + 1), L);
+                }
+                w = hadamard32_f(w, lane);
+                const float f = (1.0f / 32.0f) / L;
+                const half2 o2 = __floats2half2_rn(w.x * f, w.y * f);
+                reinterpret_cast<half2*>(P.out + (((size_t)b * P.q_len + i) * P.H + h) * HD + warp * 64)[lane] = o2;
+                if (P.out_xp) {
+                    const int n = h * HD + warp * 64 + 2 * lane, m = b * P.q_len + i;
+                    const int k0 = P.out_invperm ? (int)P.out_invperm[n] : n, k1 = P.out_invperm ? (int)P.out_invperm[n + 1] : n + 1;
+                    if (P.out_plain) {
+                        P.out_xp[k0] = __low2half(o2);
+                        P.out_xp[k1] = __high2half(o2);
+                    } else {
+                        P.out_xp[(size_t)(k0 >> 3) * 64 + m * 8 + (k0 & 7)] = __low2half(o2);
+                        P.out_xp[(size_t)(k1 >> 3) * 64 + m * 8 + (k1 & 7)] = __high2half(o2);
+                    }
+                }
+            }
+            return;
+        }
         if (warp < UNITS) {
             float2 w = make_float2(0.f, 0.f);
 #pragma unroll
@@ -404,6 +480,14 @@ extern "C" int exl2b_paged_attn_status(int device, int* status) {
     if (!g_attn_err[device]) return 0;
     EXL2B_CUDA(cudaSetDevice(device));
     EXL2B_CUDA(cudaMemcpy(status, g_attn_err[device], sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int exl2b_paged_attn_clear_status(int device) {
+    EXL2B_REQUIRE(device >= 0 && device < 64, "bad argument");
+    if (!g_attn_err[device]) return 0;
+    EXL2B_CUDA(cudaSetDevice(device));
+    EXL2B_CUDA(cudaMemset(g_attn_err[device], 0, sizeof(int)));
     return 0;
 }
 
@@ -461,9 +545,39 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
         }
         P.err = g_attn_err[dev];
     }
+    // split-KV: only for single-query decode over caches long enough to need it; grid.z CTAs per (head, sequence)
+    int nsplit = 1;
+    if (q_len == 1 && P.max_ctx > 2 * AQ_SPLIT_MIN) {
+        const int sms = device_sm_count(dev);
+        const int by_ctx = (P.max_ctx + AQ_SPLIT_MIN - 1) / AQ_SPLIT_MIN;
+        const int by_sms = std::max(1, (2 * sms) / std::max(1, num_heads * batch));
+        nsplit = std::max(1, std::min(std::min(by_ctx, by_sms), 16));
+    }
+    static float* g_ws[64] = {nullptr};
+    static unsigned int* g_cnt[64] = {nullptr};
+    static size_t g_ws_floats[64] = {0}, g_cnt_n[64] = {0};
+    if (nsplit > 1) {
+        EXL2B_REQUIRE(dev >= 0 && dev < 64, "bad device");
+        const size_t need = (size_t)batch * num_heads * nsplit * (head_dim + 2), need_c = (size_t)batch * num_heads;
+        if (g_ws_floats[dev] < need) {
+            if (g_ws[dev]) cudaFree(g_ws[dev]);
+            EXL2B_CUDA(cudaMalloc(&g_ws[dev], need * sizeof(float)));
+            g_ws_floats[dev] = need;
+        }
+        if (g_cnt_n[dev] < need_c) {
+            if (g_cnt[dev]) cudaFree(g_cnt[dev]);
+            EXL2B_CUDA(cudaMalloc(&g_cnt[dev], need_c * sizeof(unsigned)));
+            EXL2B_CUDA(cudaMemset(g_cnt[dev], 0, need_c * sizeof(unsigned)));
+            g_cnt_n[dev] = need_c;
+        }
+        P.ws = g_ws[dev];
+        P.cnt = g_cnt[dev];
+    }
+    P.nsplit = nsplit;
+    const int sc_len = nsplit > 1 ? std::max(AQ_SPLIT_MIN, (P.max_ctx + nsplit) / nsplit) + 8 : P.max_ctx + q_len;
     const int hd = head_dim;
     const size_t smem = (size_t)(hd + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
-                        (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)(P.max_ctx + q_len) * 4;
+                        (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)sc_len * 4;
     EXL2B_REQUIRE(smem <= 200 * 1024, "context of %d tokens does not fit the score buffer", P.max_ctx);
     static bool attr_set[64] = {false};
     if (!attr_set[dev]) {
@@ -471,7 +585,7 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
         EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[dev] = true;
     }
-    dim3 grid(num_heads, batch);
+    dim3 grid(num_heads, batch, nsplit);
     if (head_dim == 128)
         EXL2B_CUDA(launch_pdl(attn_q4_kernel<128>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
     else

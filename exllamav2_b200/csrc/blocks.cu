@@ -144,6 +144,29 @@ extern "C" int exl2b_qattn_forward_1_ex(exl2b_qattn_t h, const uint16_t* x, int 
                            d.num_kv_heads, past_len, past_lens, neox, d.sincos_size);
     }
     if (rope) EXL2B_REQUIRE(sin && cos, "rope needs sin/cos tables");
+    if (rows > GEMM_BIG_MIN_ROWS && !input_prepared && gemm_big_available()) {
+        // prefill rows: the reference's own sequence (q_attn.cu:153-300) -- rms_norm, three GEMMs, rope -- with the GEMMs on the
+        // tensor cores (gemm_big.cu)
+        const half* xin = (const half*)x;
+        half* xn = nullptr;
+        if (d.layernorm) {
+            EXL2B_CUDA(cudaMallocAsync(&xn, (size_t)rows * d.hidden_size * sizeof(half), stream));
+            int rc = exl2b_rms_norm(x, d.layernorm, (uint16_t*)xn, d.norm_epsilon, rows, d.hidden_size, stream_);
+            if (rc) return rc;
+            xin = xn;
+        }
+        int rc = gemm_big_launch(mq, xin, d.hidden_size, (half*)q, mq->v.N, rows, 1, stream);
+        if (!rc) rc = gemm_big_launch(mk, xin, d.hidden_size, (half*)k, mk->v.N, rows, 1, stream);
+        if (!rc) rc = gemm_big_launch(mv, xin, d.hidden_size, (half*)v, mv->v.N, rows, 1, stream);
+        if (xn) cudaFreeAsync(xn, stream);
+        if (rc || !rope) return rc;
+        const int neox = d.rope_style == 2;
+        rc = rope_launch(stream, (half*)q, (const half*)sin, (const half*)cos, batch, q_len * d.num_heads, d.head_dim, d.num_heads,
+                         past_len, past_lens, neox, d.sincos_size);
+        if (rc) return rc;
+        return rope_launch(stream, (half*)k, (const half*)sin, (const half*)cos, batch, q_len * d.num_kv_heads, d.head_dim,
+                           d.num_kv_heads, past_len, past_lens, neox, d.sincos_size);
+    }
     const bool fuse = gemv_supports_extras(mats, 3, rows) && (!rope || (d.head_dim <= 128 && 128 % d.head_dim == 0 && d.sincos_size <= d.head_dim));
     EXL2B_REQUIRE(!input_prepared || fuse, "input_prepared needs the tcgen05 layout and at most %d rows", GEMV_MTOK);
     if (fuse) {
@@ -197,6 +220,8 @@ extern "C" int exl2b_qattn_forward_2_ex(exl2b_qattn_t h, uint16_t* x, const uint
         if (rc) return rc;
         return gemv_i8_launch(a->device, (cudaStream_t)stream, &o, 1, in);
     }
+    if (!want && batch * q_len > GEMM_BIG_MIN_ROWS && gemm_big_available())
+        return gemm_big_launch(mo, (const half*)attn_out, mo->v.K, (half*)x, mo->v.N, batch * q_len, a->d.has_residual ? 0 : 1, (cudaStream_t)stream);
     if (!want) return gemv_launch(a->device, (cudaStream_t)stream, &m, 1, batch * q_len, nullptr, 0.f, EPI_STORE);
     EXL2B_REQUIRE(gemv_supports_extras(&m, 1, batch * q_len), "chained launches need the tcgen05 layout and at most %d rows", GEMV_MTOK);
     GemvExtras ex = {};
@@ -282,6 +307,29 @@ extern "C" int exl2b_qmlp_forward_ex(exl2b_qmlp_t h, uint16_t* x, int rows, uint
         if (rc) return rc;
         const I8Input in2 = {dn->xp_buf, dn->xp_buf + dn->v.K, nullptr, 0.f, d.act_gelu ? I8_GELU_MUL : I8_SILU_MUL, 1};
         return gemv_i8_launch(m->device, stream, &od, 1, in2);
+    }
+    if (rows > GEMM_BIG_MIN_ROWS && !input_prepared && !(next && next->num_consumers > 0) && gemm_big_available()) {
+        // prefill rows: rms_norm, gate and up GEMMs, act*mul, down GEMM (+residual) as in q_mlp.cu:78-236, GEMMs on the tensor cores
+        const half* xin = (const half*)x;
+        half *xn = nullptr, *tb = (half*)temp_b;
+        bool own_tb = false;
+        if (d.layernorm) {
+            EXL2B_CUDA(cudaMallocAsync(&xn, (size_t)rows * d.hidden_size * sizeof(half), stream));
+            int rc = exl2b_rms_norm(x, d.layernorm, (uint16_t*)xn, d.norm_epsilon, rows, d.hidden_size, stream_);
+            if (rc) return rc;
+            xin = xn;
+        }
+        if (!tb) {
+            EXL2B_CUDA(cudaMallocAsync(&tb, (size_t)rows * d.intermediate_size * sizeof(half), stream));
+            own_tb = true;
+        }
+        int rc = gemm_big_launch(g, xin, d.hidden_size, (half*)temp_a, d.intermediate_size, rows, 1, stream);
+        if (!rc) rc = gemm_big_launch(u, xin, d.hidden_size, tb, d.intermediate_size, rows, 1, stream);
+        if (!rc) rc = exl2b_act_mul(temp_a, (const uint16_t*)tb, rows, d.intermediate_size, d.act_gelu, stream_);
+        if (!rc) rc = gemm_big_launch(dn, (const half*)temp_a, d.intermediate_size, (half*)x, d.hidden_size, rows, d.has_residual ? 0 : 1, stream);
+        if (xn) cudaFreeAsync(xn, stream);
+        if (own_tb) cudaFreeAsync(tb, stream);
+        return rc;
     }
     const int epi = d.act_gelu ? EPI_GELU_MUL : EPI_SILU_MUL;
     const bool fuse = gemv_supports_extras(gu, 2, rows) && gemv_supports_extras(&down, 1, rows);

@@ -661,6 +661,8 @@ extern "C" int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int 
         const I8Input in = {(const half*)a, nullptr, nullptr, 0.f, I8_PLAIN};
         return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
     }
+    if (m > GEMM_BIG_MIN_ROWS && gemm_big_available())      // prefill rows: reconstruct + tensor-core GEMM (q_gemm.cu:233-266)
+        return gemm_big_launch(q, (const half*)a, lda, (half*)c, ldc, m, clear ? 1 : 0, (cudaStream_t)stream);
     GemvMat mt = {};
     mt.w = q->v;
     mt.x = (const half*)a;

@@ -84,6 +84,12 @@ struct GemvParams {
 // grid.y = ceil(M/4) does, cuda/q_gemm.cu:97).
 int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps,
                 int epilogue, const GemvExtras* ex = nullptr);
+// Many-row path (gemm_big.cu): reconstruct a column window + cuBLAS fp16 GEMM with fp32 accumulation.  Rows above
+// GEMM_BIG_MIN_ROWS take it (below, the packed-row kernels re-read the weights at most twice).
+constexpr int GEMM_BIG_MIN_ROWS = 16;
+bool gemm_big_available();
+int gemm_big_launch(const QMatrix* q, const half* a, int lda, half* c, int ldc, int M, int clear, cudaStream_t stream);
+
 // can `ex` be honoured for these matrices / this row count?  (tcgen05 layout, one pass)
 bool gemv_supports_extras(const GemvMat* mats, int nm, int M);
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ half exl2_scale_h(uint32_t nib, half smax) {
 
 template <int BITS>
 __device__ void reconstruct_block_exl2(const QMatView& v, const uint32_t* bp, int lane, int group, int n0, int k0,
-                                       half* __restrict__ out) {
+                                       half* __restrict__ out, int ld, int col0) {
     uint32_t mw[8], ew[4], A[16];
     load_block_words<BITS>(bp, lane, mw, ew);
     dequant_block_exl2<BITS>(mw, ew, A);
@@ -141,13 +141,15 @@ __device__ void reconstruct_block_exl2(const QMatView& v, const uint32_t* bp, in
         for (int e = 0; e < 2; ++e) {
             const int kp = k0 + value_pos_l(v.layout, lane, p * 2 + e).k_local;
             const int row = v.perm ? (int)v.perm[kp] : kp;
-            out[(size_t)row * v.N + n] = e ? __high2half(w2) : __low2half(w2);
+            out[(size_t)row * ld + (n - col0)] = e ? __high2half(w2) : __low2half(w2);
         }
     }
 }
 
-__global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restrict__ out) {
-    const int ks = blockIdx.x, strip = blockIdx.y;
+// out[row * ld + (n - col0)] for the strips [strip0, strip0 + gridDim.y): the whole matrix (ld = N, col0 = 0, strip0 = 0) for
+// exl2b_reconstruct, or a column window for the large-M path (gemm_big.cu)
+__global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restrict__ out, int ld, int col0, int strip0) {
+    const int ks = blockIdx.x, strip = strip0 + blockIdx.y;
     const int blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint2 tab = v.slab_tab[ks];
     const int bits = (tab.y >> 16) & 0xF, group = tab.y & 0xFFFF;
@@ -155,12 +157,12 @@ __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restr
     const int n0 = strip * strip_n(v.layout) + blk * BLOCK_N, k0 = ks * SLAB_K;
     if (!v.is_gptq) {
         switch (bits) {
-            case 2: reconstruct_block_exl2<2>(v, bp, lane, group, n0, k0, out); break;
-            case 3: reconstruct_block_exl2<3>(v, bp, lane, group, n0, k0, out); break;
-            case 4: reconstruct_block_exl2<4>(v, bp, lane, group, n0, k0, out); break;
-            case 5: reconstruct_block_exl2<5>(v, bp, lane, group, n0, k0, out); break;
-            case 6: reconstruct_block_exl2<6>(v, bp, lane, group, n0, k0, out); break;
-            case 8: reconstruct_block_exl2<8>(v, bp, lane, group, n0, k0, out); break;
+            case 2: reconstruct_block_exl2<2>(v, bp, lane, group, n0, k0, out, ld, col0); break;
+            case 3: reconstruct_block_exl2<3>(v, bp, lane, group, n0, k0, out, ld, col0); break;
+            case 4: reconstruct_block_exl2<4>(v, bp, lane, group, n0, k0, out, ld, col0); break;
+            case 5: reconstruct_block_exl2<5>(v, bp, lane, group, n0, k0, out, ld, col0); break;
+            case 6: reconstruct_block_exl2<6>(v, bp, lane, group, n0, k0, out, ld, col0); break;
+            case 8: reconstruct_block_exl2<8>(v, bp, lane, group, n0, k0, out, ld, col0); break;
         }
     } else {
         uint32_t mw[8], ew[4];
@@ -181,7 +183,7 @@ __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restr
             for (int e = 0; e < 2; ++e) {
                 const int kp = k0 + value_pos_l(v.layout, lane, p * 2 + e).k_local;
                 const int row = v.perm ? (int)v.perm[kp] : kp;
-                out[(size_t)row * v.N + n] = e ? __high2half(w2) : __low2half(w2);
+                out[(size_t)row * ld + (n - col0)] = e ? __high2half(w2) : __low2half(w2);
             }
         }
     }
@@ -482,13 +484,24 @@ extern "C" int exl2b_qmatrix_info(exl2b_qmatrix_t h, int* height, int* width, in
     return 0;
 }
 
+namespace exl2b {
+// columns [strip0 * strip_n, (strip0 + nstrips) * strip_n) of the dequantised matrix into out[K, ld] (original row order)
+int reconstruct_window(const QMatrix* m, half* out, int ld, int strip0, int nstrips, cudaStream_t stream) {
+    dim3 grid(m->v.KS, nstrips), block(32 * strip_blocks(m->v.layout));
+    reconstruct_kernel<<<grid, block, 0, stream>>>(m->v, 0, out, ld, strip0 * strip_n(m->v.layout), strip0);
+    g_launch_count++;
+    EXL2B_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // namespace exl2b
+
 extern "C" int exl2b_reconstruct(exl2b_qmatrix_t h, uint16_t* out, exl2b_stream_t stream) {
     QMatrix* m = (QMatrix*)h;
     EXL2B_REQUIRE(m && out, "null argument");
     EXL2B_CUDA(cudaSetDevice(m->device));
     int gs = 0;
     dim3 grid(m->v.KS, m->v.strips), block(32 * strip_blocks(m->v.layout));
-    reconstruct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(m->v, gs, (half*)out);
+    reconstruct_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(m->v, gs, (half*)out, m->v.N, 0, 0);
     g_launch_count++;
     EXL2B_CUDA(cudaGetLastError());
     return 0;

@@ -91,6 +91,7 @@ _sig("exl2b_qmlp_forward_gateup", c_int, c_void_p, c_void_p, c_int, c_void_p, c_
 _sig("exl2b_paged_attn_decode_q4", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p]))
 _sig("exl2b_paged_attn_decode_q4_ex", c_int, *([c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]))
 _sig("exl2b_paged_attn_status", c_int, c_int, POINTER(c_int))
+_sig("exl2b_paged_attn_clear_status", c_int, c_int)
 
 
 class _Chain(Structure):
@@ -524,6 +525,10 @@ def paged_attn_decode_q4(q, k_new, v_new, k_cache, k_scales, v_cache, v_scales, 
         _p(cache_seqlens), _p(block_table), _p(out), B, q_len, H, KVH, hd, k_cache.shape[1], block_table.shape[1],
         float(softmax_scale), out_consumer or None, _p(sin), _p(cos), int(style), sin.shape[-1] if sin is not None else 0,
         _stream(q)))
+
+
+def paged_attn_clear_status(device) -> None:
+    _check(lib.exl2b_paged_attn_clear_status(torch.device(device).index or 0))
 
 
 def paged_attn_status(device) -> int:

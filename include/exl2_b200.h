@@ -202,6 +202,7 @@ int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* k_new, cons
 /* Sticky status of the fused attention kernels on `device` (synchronises): bit 0 = a sequence would have run past its page
  * table (cache_seqlens[b] + q_len > pages_per_seq * page_size); that call appended nothing and wrote no output. */
 int exl2b_paged_attn_status(int device, int* status);
+int exl2b_paged_attn_clear_status(int device);
 
 /* ---- chained launches (no reference counterpart; the reference runs norm / projection / rope / activation as separate
  * kernels, q_attn.cu:153-345, q_mlp.cu:78-236).  A producer's epilogue can write its output straight into the

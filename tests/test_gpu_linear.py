@@ -174,3 +174,53 @@ def test_full_size_properties(name, kw):
     t = lin.forward((a1.float() + a2.float()).half()).float()
     assert (torch.linalg.norm(s - t) / torch.linalg.norm(t)).item() <= 2e-3
     lin.unload()
+
+
+# ---- many rows (prefill): reconstruct + tensor-core GEMM, the reference's regime above MAX_Q_GEMM_ROWS (q_gemm.cu:233-266) ------
+
+@pytest.mark.parametrize("name", ["b4_g128", "b54_g64", "b865_mixed", "b6_g128_bias", "b4_n96_ragged", "gptq_g128_act", "gptq_g64_act_b", "gptq_g32"])
+@pytest.mark.parametrize("M", [17, 32, 33, 64, 256])
+def test_gemm_many_rows(name, M):
+    lin, w_np = _load(name)
+    a = cases.activations(name, M)
+    truth = oracle.gemm_truth(a, _oracle_w(name, w_np), w_np.get("bias"))
+    got = lin.forward(torch.from_numpy(a).to(DEV)).cpu().numpy()
+    err = oracle.rel_l2(got, truth)
+    assert err <= GEMM_TOL, f"{name} M={M}: rel_l2 {err:.2e}"
+    lin.unload()
+
+
+def test_gemm_many_rows_accumulate_strided():
+    from exllamav2_b200 import ext as ext_c
+    name = "b6_g128_bias"
+    lin, w_np = _load(name)
+    K, N = cases.case_shape(name)
+    M = 40
+    a = cases.activations(name, M)
+    c0 = np.random.default_rng(6).normal(0, 1, size=(M, N)).astype(np.float16)
+    a_buf = torch.zeros((M, K + 8), dtype=torch.half, device=DEV)
+    a_buf[:, :K] = torch.from_numpy(a).to(DEV)
+    c_buf = torch.zeros((M, N + 16), dtype=torch.half, device=DEV)
+    c_buf[:, :N] = torch.from_numpy(c0).to(DEV)
+    ext_c.gemm_half_q_half_accum(a_buf[:, :K], lin.q_handle, c_buf[:, :N])
+    truth = oracle.gemm_truth(a, _oracle_w(name, w_np), w_np.get("bias"), c0)
+    assert oracle.rel_l2(c_buf[:, :N].cpu().numpy(), truth) <= GEMM_TOL
+    assert torch.count_nonzero(c_buf[:, N:]).item() == 0
+    lin.unload()
+
+
+def test_prefill_2048_rows_llama_shape():
+    """BASELINE config 3 'bs=16 prefill': 2048 rows through a 4096 x 4096 [5,4] matrix in ONE weight pass; checked against an
+    fp32 matmul over the kernel's own (bit-exact) reconstruct."""
+    import math
+    from exllamav2_b200 import synthetic
+    from exllamav2_b200.linear import ExLlamaV2Linear
+    w = synthetic.random_exl2(4096, 4096, (5, 4), (0.1, 0.9), 128, device=DEV, seed=9, weight_std=1.0 / math.sqrt(4096))
+    lin = ExLlamaV2Linear(4096, 4096, device=DEV)
+    lin.load(w)
+    a = torch.randn((2048, 4096), device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)).half()
+    y = lin.forward(a)
+    ref = a.float() @ lin.get_weight_tensor_dq().float()
+    err = (torch.linalg.norm(y.float() - ref) / torch.linalg.norm(ref)).item()
+    assert err <= GEMM_TOL, f"rel_l2 {err:.2e}"
+    lin.unload()
