@@ -369,6 +369,15 @@ extern "C" int exl2b_qmlp_forward_gateup(exl2b_qmlp_t h, const uint16_t* x, int 
     EXL2B_CUDA(cudaSetDevice(m->device));
     const exl2b_qmlp_desc& d = m->d;
     const QMatrix *g = (const QMatrix*)d.gate, *u = (const QMatrix*)d.up;
+    if (rows == 1 && m->i8_gu && gemv_i8_enabled()) {
+        // decode row: gate|up as one integer-GEMV launch (RMSNorm in its prologue), then act(gate) * up on the rank's slice
+        if (!m->up_scratch) EXL2B_CUDA(cudaMalloc(&m->up_scratch, (size_t)d.intermediate_size * sizeof(half)));
+        const I8Out o[2] = {{g, (half*)temp_a, 1}, {u, m->up_scratch, 1}};
+        const I8Input in = {(const half*)x, nullptr, (const half*)d.layernorm, d.norm_epsilon, d.layernorm ? I8_RMSNORM : I8_PLAIN, 0};
+        int rc = gemv_i8_launch(m->device, (cudaStream_t)stream_, o, 2, in);
+        if (rc) return rc;
+        return exl2b_act_mul(temp_a, (const uint16_t*)m->up_scratch, 1, d.intermediate_size, d.act_gelu, stream_);
+    }
     GemvMat gu[2] = {
         make_mat(g, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),
         make_mat(u, (const half*)x, d.hidden_size, (half*)temp_a, d.intermediate_size, 1),

@@ -1,520 +1,15 @@
-// Streaming dequant-GEMV for 1..8 tokens per pass: the B200-native replacement of gemm_half_q_half_kernel
-// (exllamav2_ext/cuda/q_gemm_kernel.cuh:140-565) and gemm_half_q_half_gptq_kernel (q_gemm_kernel_gptq.cuh:61-246).
-//
-// Design:
-//   * stream-K: the launch's unit space (matrix, strip, slab) is cut into gridDim.x equal contiguous ranges, so
-//     every CTA streams the same number of bytes whatever the matrix shape; a range is 1..n "segments", each a
-//     contiguous byte range of ONE strip's stream.
-//   * inside a CTA each of the 8 warps owns a contiguous sub-range of the segment and is its own producer and
-//     consumer: lane 0 issues cp.async.bulk (TMA 1-D) copies of whole slabs into the warp's private 3-stage
-//     shared-memory ring, completion on per-stage mbarriers; no CTA-wide barrier in the main loop.
-//   * everything static (weights, permutation entries, norm weights) is requested BEFORE griddepcontrol.wait: with
-//     programmatic dependent launch this GEMV's weights are in flight while the previous kernel (which produces our
-//     activations) drains.  All slab bookkeeping is arithmetic on kernel parameters (QRegion), never a table load.
-//   * activations are gathered through q_perm (optionally with the RMSNorm folded in) into shared memory once
-//     per segment; weights are unpacked in the fp16 domain straight into mma.m16n8k16 A fragments, tokens are
-//     the N=8 dimension, accumulation is fp32 in registers, group scales are applied per group in fp32.
-//   * split-K partial sums go through a small fp32 workspace; the LAST CTA to arrive for a strip reduces them in
-//     a fixed order (deterministic, no fp16 atomics -- the reference's atomicAdd(half2), q_gemm_kernel.cuh:560,
-//     is not bit-reproducible) and applies the epilogue (bias / residual add / silu(gate)*up).
+// Dispatch of gemm_half_q_half over the row count, and the split-K workspace of the tcgen05 kernel.
+//   1 row        -> gemv_i8.cu   (HBM-bound integer GEMV, the decode path)
+//   2 .. 16 rows -> gemm_tc.cu   (packed weights as the tcgen05 A operand from tensor memory, 8 rows per pass)
+//   more         -> gemm_big.cu  (reconstruct window + dense tensor-core GEMM: the reference's regime above MAX_Q_GEMM_ROWS)
+// Replaces gemm_half_q_half_cuda (exllamav2_ext/cuda/q_gemm.cu:201-313).
 #include <algorithm>
 #include <mutex>
 
-#include "dequant.cuh"
 #include "gemv.cuh"
 #include "gemv_i8.cuh"
 
 namespace exl2b {
-
-constexpr int GEMV_WARPS = 8;
-constexpr int GEMV_THREADS = GEMV_WARPS * 32;
-constexpr int STAGE_BYTES = 4096;
-constexpr int STAGES = 3;
-constexpr int RING_BYTES = STAGE_BYTES * STAGES;          // per warp
-constexpr int SMEM_RINGS = GEMV_WARPS * RING_BYTES;       // 96 KB
-constexpr int SMEM_BARS = GEMV_WARPS * STAGES * 8;
-constexpr int SMEM_MISC = 64;                              // rstd[8] + flag
-constexpr int RED_FLOATS = GEMV_MTOK * STRIP_N;           // workspace floats per (strip, contributor)
-
-__host__ __device__ __forceinline__ int run_max(int bits) { return STAGE_BYTES / slab_bytes(bits); }
-
-__device__ __forceinline__ int cta_of_unit(unsigned x, unsigned G, unsigned U) { return (int)(((x + 1u) * G - 1u) / U); }
-
-__device__ __forceinline__ int region_of(const QMatView& w, int ks) {
-    int r = 0;
-#pragma unroll
-    for (int i = 1; i < MAX_REGIONS; ++i)
-        if (i < w.num_regions && ks >= w.reg[i].ks_begin) r = i;
-    return r;
-}
-__device__ __forceinline__ int region_end(const QMatView& w, int r) { return (r + 1 < w.num_regions) ? w.reg[r + 1].ks_begin : w.KS; }
-
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// diagnostics: per-launch slot of 8 u64: [0..5] phase stamps (ns) of CTA dbg_cta, [6] min start, [7] max end over all CTAs
-#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == P.dbg_cta && tid == 0) { P.dbg[i] = gtimer(); } } while (0)
-
-// ---- per-slab math ---------------------------------------------------------------------------------------------
-
-template <int BITS>
-__device__ __forceinline__ void load_lane_words(const uint8_t* base, int lane, uint32_t* mw, uint32_t* ew) {
-    constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
-    if constexpr (Pm == 8) {
-        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16), b = *reinterpret_cast<const uint4*>(base + 512 + lane * 16);
-        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w; mw[4] = b.x; mw[5] = b.y; mw[6] = b.z; mw[7] = b.w;
-    } else if constexpr (Pm == 4) {
-        const uint4 a = *reinterpret_cast<const uint4*>(base + lane * 16);
-        mw[0] = a.x; mw[1] = a.y; mw[2] = a.z; mw[3] = a.w;
-    } else {
-        const uint2 a = *reinterpret_cast<const uint2*>(base + lane * 8);
-        mw[0] = a.x; mw[1] = a.y;
-    }
-    if constexpr (Pe == 1) {
-        ew[0] = *reinterpret_cast<const uint32_t*>(base + 128 * Pm + lane * 4);
-    } else if constexpr (Pe == 2) {
-        const uint2 a = *reinterpret_cast<const uint2*>(base + 128 * Pm + lane * 8);
-        ew[0] = a.x; ew[1] = a.y;
-    }
-}
-
-__device__ __forceinline__ void mma_block(float (&acc)[2][4], const uint32_t* A, const uint32_t (&B)[4]) {
-#pragma unroll
-    for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-        for (int s = 0; s < 2; ++s) mma16816(acc[sub], &A[(sub * 2 + s) * 4], B[2 * s], B[2 * s + 1]);
-}
-
-// ---- activation functions (reference arithmetic, cuda/q_mlp_activation.cuh:13-52) -------------------------------
-__device__ __forceinline__ half silu_h(half x) {
-    half e = hexp(__hneg(x));
-    half r = hrcp(__hadd(__float2half(1.0f), e));
-    return __hmul(x, r);
-}
-__device__ __forceinline__ half gelu_h(half x) {
-    float xf = __half2float(x);
-    const float c = 0.797884560803f;
-    float t = c * (xf + 0.044715f * xf * xf * xf);
-    float th;   // tanh_opt of the reference (cuda/q_mlp_activation.cuh:4-11): tanh.approx on sm_75+
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
-    xf = 0.5f * xf * (1.0 + th);
-    return __float2half_rn(xf);
-}
-
-// Per-warp accumulation state of one segment.
-struct WarpAcc {
-    float tot[2][2][4];     // [blk][sub][mma c-reg]
-    float grp[2][2][4];     // accumulates the current group only
-    float sacc[4];          // 4-bit offset form: sum of the group's activations per token (all-ones mma row)
-    uint32_t sw[8];         // EXL2: scale words of (group, strip); GPTQ: zero words
-    half gsc[8];            // GPTQ: fp16 scales of the lane's 8 columns
-    half smax;
-    int cur_group;
-    int cur_bits;
-};
-
-__device__ __forceinline__ void acc_flush(WarpAcc& a, const QMatView& w, int g) {     // tot += scale(group, n) * grp
-#pragma unroll
-    for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int j = 4 * blk + 2 * sub + rr;
-                const int nib = (int)((a.sw[j] >> (4 * g)) & 15u);
-                float s, coff;
-                if (!w.is_gptq) {
-                    const int q = nib + 1;
-                    s = __half2float(__hmul(__int2half_rn(q * q), a.smax));     // fp16 scale, qdq_util.cuh:24-30
-                    coff = (a.cur_bits == 4) ? (float)(OFFSET4 + 8) : 0.f;      // offset form: A = 64 + q, zero point 8
-                } else {
-                    s = __half2float(a.gsc[j]);
-                    coff = (float)(OFFSET4 + nib + 1);                          // zero + 1, q_gemm_kernel_gptq.cuh:169
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float v = fmaf(-coff, a.sacc[e], a.grp[blk][sub][2 * rr + e]);
-                    a.tot[blk][sub][2 * rr + e] = fmaf(s, v, a.tot[blk][sub][2 * rr + e]);
-                    a.grp[blk][sub][2 * rr + e] = 0.f;
-                }
-            }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) a.sacc[e] = 0.f;
-}
-
-__device__ __forceinline__ void acc_enter_group(WarpAcc& a, const QMatView& w, int grp, int strip, int g, int bits) {
-    a.cur_group = grp;
-    a.cur_bits = bits;
-    const int n_words = w.N >> 3;
-    const uint32_t* src = (w.is_gptq ? w.qzeros : w.q_scale) + (size_t)grp * n_words + strip * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a.sw[j] = (strip * 8 + j < n_words) ? __ldg(src + j) : 0u;
-    if (!w.is_gptq) {
-        a.smax = __ldg(w.q_scale_max + grp);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = strip * STRIP_N + (j >> 2) * 32 + ((j >> 1) & 1) * 16 + (j & 1) * 8 + g;
-            a.gsc[j] = (n < w.N) ? __ldg(w.gptq_scales + (size_t)grp * w.N + n) : __float2half(0.f);
-        }
-    }
-}
-
-// Consume `run` slabs of one region that sit contiguously at `sp` in shared memory.
-//   d0: index of the first slab inside its region, bptr: this lane's B-fragment source for the first slab.
-template <int BITS, bool GPTQ>
-__device__ __forceinline__ void consume_run(WarpAcc& a, const QMatView& w, const QRegion& R, const uint8_t* sp, int run, int d0,
-                                            const uint8_t* bptr, bool has_b, int strip, int lane) {
-    const int g = lane >> 2;
-    const int gmask = (1 << R.spg_log2) - 1;
-#pragma unroll 2
-    for (int i = 0; i < run; ++i) {
-        const int d = d0 + i;
-        if (a.cur_group < 0 || (d & gmask) == 0) {
-            if (a.cur_group >= 0) acc_flush(a, w, g);
-            acc_enter_group(a, w, R.group_base + (d >> R.spg_log2), strip, g, BITS);
-        }
-        uint32_t B[4] = {0u, 0u, 0u, 0u};
-        if (has_b) {
-            const uint4 b4 = *reinterpret_cast<const uint4*>(bptr + i * (SLAB_K * 2));
-            B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w;
-        }
-        if constexpr (BITS == 4) {          // offset form: the all-ones row yields sum_k a[k] per token
-            const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};
-            mma16816(a.sacc, ones, B[0], B[1]);
-            mma16816(a.sacc, ones, B[2], B[3]);
-        }
-        const uint8_t* sm = sp + i * slab_bytes(BITS);
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-            uint32_t mw[8], ew[2], A[16];
-            load_lane_words<BITS>(sm + blk * block_bytes(BITS), lane, mw, ew);
-            if constexpr (BITS == 4) dequant_block_4bit_offset(mw, A);
-            else dequant_block_exl2<BITS>(mw, ew, A);
-            mma_block(a.grp[blk], A, B);
-        }
-    }
-}
-
-// ---- the kernel ----------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const __grid_constant__ GemvParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-
-    griddep_launch_dependents();   // let the next kernel in the stream start prefetching its weights
-    DBG_STAMP(0);
-    if (P.dbg && tid == 0) atomicMin(P.dbg + 6, gtimer());
-
-    const uint32_t smem0 = smem_addr(smem);
-    const uint32_t ring = smem0 + warp * RING_BYTES;
-    const uint32_t bars = smem0 + SMEM_RINGS + warp * STAGES * 8;
-    uint8_t* ring_p = smem + warp * RING_BYTES;
-    float* rstd_s = reinterpret_cast<float*>(smem + SMEM_RINGS + SMEM_BARS);
-    int* flag_s = reinterpret_cast<int*>(smem + SMEM_RINGS + SMEM_BARS + 32);
-    uint8_t* act_s = smem + SMEM_RINGS + SMEM_BARS + SMEM_MISC;
-    const int M = P.M, KS = P.KS;
-    float* red_s = reinterpret_cast<float*>(act_s + (size_t)M * P.act_stride);      // [warp][tok][64], generic proxy only
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    const unsigned U = (unsigned)P.total_units, G = gridDim.x;
-    const int u0 = (int)((unsigned)blockIdx.x * U / G), u1 = (int)(((unsigned)blockIdx.x + 1u) * U / G);
-
-    uint32_t phases = 0;          // parity bit per stage
-    bool first_seg = true;
-    int u = u0;
-    while (u < u1) {
-        int mi = 0;
-        while (mi + 1 < P.num_mats && u >= P.mat[mi + 1].unit_begin) ++mi;
-        const GemvMat& mt = P.mat[mi];
-        const QMatView& w = mt.w;
-        const int local = u - mt.unit_begin;
-        const int strip = local / KS, ks0 = local - strip * KS;
-        const int seg = min(KS - ks0, u1 - u);
-        const int wk0 = ks0 + (seg * warp) / GEMV_WARPS, wk1 = ks0 + (seg * (warp + 1)) / GEMV_WARPS;
-        const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(w.packed) + (size_t)strip * w.strip_bytes;
-
-        // ---- producer: fill the ring (weights never depend on a previous kernel) ----
-        int fetch_ks = wk0, fstage = 0, cstage = 0;
-        auto issue = [&]() {
-            const int r = region_of(w, fetch_ks);
-            const QRegion& R = w.reg[r];
-            const int run = min(min(run_max(R.bits), region_end(w, r) - fetch_ks), wk1 - fetch_ks);
-            const uint32_t bytes = (uint32_t)run * slab_bytes(R.bits);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bars + 8 * fstage, bytes);
-                bulk_copy_g2s(ring + fstage * STAGE_BYTES, gsrc + R.off_base + (uint32_t)(fetch_ks - R.ks_begin) * slab_bytes(R.bits),
-                              bytes, bars + 8 * fstage);
-            }
-            fetch_ks += run;
-            fstage = (fstage + 1 == STAGES) ? 0 : fstage + 1;
-        };
-#pragma unroll 1
-        for (int s = 0; s < STAGES && fetch_ks < wk1; ++s) issue();
-
-        // static data of the activation gather, fetched BEFORE the dependency wait: the permutation entries of the
-        // rows this thread stages (q_perm never changes) and, with the norm folded in, the norm weights
-        constexpr int PRE = 8;
-        const int rows = seg * SLAB_K, k0 = ks0 * SLAB_K;
-        int src_pre[PRE];
-        half nw_pre[PRE];
-#pragma unroll
-        for (int j = 0; j < PRE; ++j) {
-            const int r = tid + j * GEMV_THREADS;
-            src_pre[j] = 0;
-            nw_pre[j] = __float2half(0.f);
-            if (r < rows) src_pre[j] = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
-        }
-        if (P.norm_w) {
-#pragma unroll
-            for (int j = 0; j < PRE; ++j)
-                if (tid + j * GEMV_THREADS < rows) nw_pre[j] = __ldg(P.norm_w + src_pre[j]);
-        }
-        DBG_STAMP(1);
-
-        if (first_seg) griddep_wait();   // from here on we may read what the previous kernel wrote
-        DBG_STAMP(2);
-
-        // ---- stage activations a'[m][r] = f(x[m][perm[k0+r]]) for the segment's rows ----
-        if (first_seg && P.norm_w) {
-            // RMSNorm statistics per token (cuda/rms_norm.cu:55-111): clamp, fp32 sum of squares, rsqrt(mean+eps)
-            const int K = w.K;
-            if (M == 1) {          // single token: all 256 threads share the row, 128-bit loads
-                float sum = 0.f;
-                for (int k = tid * 8; k < K; k += GEMV_THREADS * 8) {
-                    const uint4 v4 = *reinterpret_cast<const uint4*>(mt.x + k);
-                    const half2* h2 = reinterpret_cast<const half2*>(&v4);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
-                        float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
-                        sum = fmaf(f0, f0, sum);
-                        sum = fmaf(f1, f1, sum);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0) red_s[warp] = sum;
-                __syncthreads();
-                if (tid == 0) {
-                    float tot = 0.f;
-#pragma unroll
-                    for (int i = 0; i < GEMV_WARPS; ++i) tot += red_s[i];
-                    rstd_s[0] = rsqrtf(tot * (1.0f / (float)K) + P.norm_eps);
-                }
-            } else {
-                for (int m = warp; m < M; m += GEMV_WARPS) {
-                    const half* xr = mt.x + (size_t)m * mt.ldx;
-                    float sum = 0.f;
-                    for (int k = lane * 8; k < K; k += 256) {
-                        const uint4 v4 = *reinterpret_cast<const uint4*>(xr + k);
-                        const half2* h2 = reinterpret_cast<const half2*>(&v4);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float f0 = fmaxf(-65504.f, fminf(__low2float(h2[i]), 65504.f));
-                            float f1 = fmaxf(-65504.f, fminf(__high2float(h2[i]), 65504.f));
-                            sum = fmaf(f0, f0, sum);
-                            sum = fmaf(f1, f1, sum);
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lane == 0) rstd_s[m] = rsqrtf(sum * (1.0f / (float)K) + P.norm_eps);
-                }
-            }
-            __syncthreads();
-        }
-        {
-            // every thread stages rows r = tid + j*256 for all M tokens; all loads of a thread are independent
-#pragma unroll
-            for (int j = 0; j < PRE; ++j) {
-                const int r = tid + j * GEMV_THREADS;
-                if (r < rows) {
-                    for (int m = 0; m < M; ++m) {
-                        half v = mt.x[(size_t)m * mt.ldx + src_pre[j]];
-                        if (P.norm_w) {
-                            float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
-                            v = __float2half_rn(xf * __half2float(nw_pre[j]) * rstd_s[m]);
-                        }
-                        *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
-                    }
-                }
-            }
-            for (int r = tid + PRE * GEMV_THREADS; r < rows; r += GEMV_THREADS) {     // long segments (> 2048 rows)
-                const int src = w.perm ? (int)__ldg(w.perm + k0 + r) : k0 + r;
-                for (int m = 0; m < M; ++m) {
-                    half v = mt.x[(size_t)m * mt.ldx + src];
-                    if (P.norm_w) {
-                        float xf = fmaxf(-65504.f, fminf(__half2float(v), 65504.f));
-                        v = __float2half_rn(xf * __half2float(__ldg(P.norm_w + src)) * rstd_s[m]);
-                    }
-                    *reinterpret_cast<half*>(act_s + (size_t)m * P.act_stride + r * 2) = v;
-                }
-            }
-        }
-        first_seg = false;
-        __syncthreads();
-        DBG_STAMP(3);
-
-        // ---- consumer ----
-        WarpAcc a;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) a.tot[i][j][c] = 0.f, a.grp[i][j][c] = 0.f;
-        a.cur_group = -1;
-        a.cur_bits = 0;
-        a.smax = __float2half(0.f);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) a.sacc[e] = 0.f;
-
-        const bool has_b = g < M;
-        const uint8_t* bbase = act_s + (size_t)g * P.act_stride + t * 16;
-        int cons_ks = wk0;
-        while (cons_ks < wk1) {
-            const int r = region_of(w, cons_ks);
-            const QRegion& R = w.reg[r];
-            const int bits = R.bits;
-            const int run = min(min(run_max(bits), region_end(w, r) - cons_ks), wk1 - cons_ks);
-            mbar_wait(bars + 8 * cstage, (phases >> cstage) & 1u);
-            phases ^= 1u << cstage;
-            const uint8_t* sp = ring_p + cstage * STAGE_BYTES;
-            const uint8_t* bptr = bbase + (cons_ks - ks0) * (SLAB_K * 2);
-            const int d0 = cons_ks - R.ks_begin;
-            if (w.is_gptq) {
-                consume_run<4, true>(a, w, R, sp, run, d0, bptr, has_b, strip, lane);
-            } else {
-                switch (bits) {
-                    case 4: consume_run<4, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                    case 5: consume_run<5, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                    case 3: consume_run<3, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                    case 6: consume_run<6, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                    case 2: consume_run<2, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                    default: consume_run<8, false>(a, w, R, sp, run, d0, bptr, has_b, strip, lane); break;
-                }
-            }
-            __syncwarp();
-            cons_ks += run;
-            cstage = (cstage + 1 == STAGES) ? 0 : cstage + 1;
-            if (fetch_ks < wk1) issue();     // refill the stage we just drained
-        }
-        if (a.cur_group >= 0) acc_flush(a, w, g);
-
-        // ---- cross-warp reduction through a dedicated (never async-written) shared-memory region ----
-        {
-            float* red = red_s + warp * (M * STRIP_N);
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int tok = 2 * t + e;
-                            if (tok < M) red[tok * STRIP_N + 32 * blk + 16 * sub + 8 * rr + g] = a.tot[blk][sub][2 * rr + e];
-                        }
-        }
-        __syncthreads();
-        DBG_STAMP(4);
-
-        const int gs = mt.strip_begin + strip;
-        const unsigned sb = (unsigned)mt.unit_begin + (unsigned)strip * KS;
-        const int first_cta = cta_of_unit(sb, G, U), last_cta = cta_of_unit(sb + KS - 1, G, U);
-        const int nc = last_cta - first_cta + 1, jc = (int)blockIdx.x - first_cta;
-        const bool paired = P.epilogue != EPI_STORE;
-        const int n_out = M * STRIP_N;
-        auto warp_sum = [&](int o) {
-            float v = 0.f;
-#pragma unroll
-            for (int wi = 0; wi < GEMV_WARPS; ++wi) v += red_s[wi * n_out + o];
-            return v;
-        };
-        auto epilogue_store = [&](int o, float v) {
-            const int tok = o >> 6, n = strip * STRIP_N + (o & 63);
-            if (n < w.N) {
-                if (w.bias) v += __half2float(w.bias[n]);
-                half* cp = mt.c + (size_t)tok * mt.ldc + n;
-                if (!mt.clear) v += __half2float(*cp);
-                *cp = __float2half_rn(v);
-            }
-        };
-
-        if (nc == 1 && !paired) {
-            for (int o = tid; o < n_out; o += GEMV_THREADS) epilogue_store(o, warp_sum(o));
-        } else {
-            float* wsp = P.ws + ((size_t)gs * P.maxc + jc) * RED_FLOATS;
-            for (int o = tid; o < n_out; o += GEMV_THREADS) __stcg(wsp + o, warp_sum(o));
-            __threadfence();
-            __syncthreads();
-            int expected = nc, cidx = gs;
-            if (paired) {
-                // gate strip j and up strip j share one counter (the gate's) and are finalised together
-                const GemvMat& other = P.mat[1 - mi];
-                const unsigned ob = (unsigned)other.unit_begin + (unsigned)strip * KS;
-                expected += cta_of_unit(ob + KS - 1, G, U) - cta_of_unit(ob, G, U) + 1;
-                cidx = P.mat[0].strip_begin + strip;
-            }
-            if (tid == 0) {
-                const unsigned int old = atomicAdd(P.counters + cidx, 1u);
-                *flag_s = (old == (unsigned int)(expected - 1)) ? 1 : 0;
-            }
-            __syncthreads();
-            if (*flag_s) {
-                __threadfence();
-                if (!paired) {
-                    const float* base = P.ws + (size_t)gs * P.maxc * RED_FLOATS;
-                    for (int o = tid; o < n_out; o += GEMV_THREADS) {
-                        float v = 0.f;
-                        for (int j = 0; j < nc; ++j) v += __ldcg(base + (size_t)j * RED_FLOATS + o);
-                        epilogue_store(o, v);
-                    }
-                } else {
-                    const GemvMat& mg = P.mat[0];
-                    const GemvMat& mu = P.mat[1];
-                    const unsigned gb = (unsigned)mg.unit_begin + (unsigned)strip * KS;
-                    const unsigned ub = (unsigned)mu.unit_begin + (unsigned)strip * KS;
-                    const int ncg = cta_of_unit(gb + KS - 1, G, U) - cta_of_unit(gb, G, U) + 1;
-                    const int ncu = cta_of_unit(ub + KS - 1, G, U) - cta_of_unit(ub, G, U) + 1;
-                    const float* bg = P.ws + (size_t)(mg.strip_begin + strip) * P.maxc * RED_FLOATS;
-                    const float* bu = P.ws + (size_t)(mu.strip_begin + strip) * P.maxc * RED_FLOATS;
-                    for (int o = tid; o < n_out; o += GEMV_THREADS) {
-                        float vg = 0.f, vu = 0.f;
-                        for (int j = 0; j < ncg; ++j) vg += __ldcg(bg + (size_t)j * RED_FLOATS + o);
-                        for (int j = 0; j < ncu; ++j) vu += __ldcg(bu + (size_t)j * RED_FLOATS + o);
-                        const int tok = o >> 6, n = strip * STRIP_N + (o & 63);
-                        if (n < mg.w.N) {
-                            if (mg.w.bias) vg += __half2float(mg.w.bias[n]);
-                            if (mu.w.bias) vu += __half2float(mu.w.bias[n]);
-                            // the reference rounds gate and up to fp16 (temp_a / temp_b) before act_mul (q_mlp.cu:187-196)
-                            const half hg = __float2half_rn(vg), hu = __float2half_rn(vu);
-                            const half av = (P.epilogue == EPI_GELU_MUL) ? gelu_h(hg) : silu_h(hg);
-                            mg.c[(size_t)tok * mg.ldc + n] = __hmul(av, hu);
-                        }
-                    }
-                }
-                if (tid == 0) P.counters[cidx] = 0u;     // ready for the next launch (stream-ordered)
-            }
-        }
-        __syncthreads();      // act / red memory is reused by the next segment
-        DBG_STAMP(5);
-        u += seg;
-    }
-    if (P.dbg && tid == 0) atomicMax(P.dbg + 7, gtimer());
-}
-
-// ---- host launcher -----------------------------------------------------------------------------------------------
 
 int g_ctas_per_sm = 2;
 int g_tc_ctas_per_sm = [] { const char* e = getenv("EXL2B_TC_CTAS"); return e ? atoi(e) : 2; }();
@@ -543,10 +38,6 @@ static int ensure_workspace(int device, DeviceWorkspace** out) {
         EXL2B_CUDA(cudaMemset(d.counters, 0, d.n_counters * sizeof(unsigned int)));
         EXL2B_CUDA(cudaDeviceSynchronize());
     }
-    if (!d.attr_set) {
-        EXL2B_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        d.attr_set = true;
-    }
     *out = &d;
     return 0;
 }
@@ -565,9 +56,10 @@ int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_b
 int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue,
                    const GemvExtras* ex);
 
+bool gemm_tc_supported(const QMatView& v);
 bool gemv_supports_extras(const GemvMat* mats, int nm, int M) {
     for (int i = 0; i < nm; ++i)
-        if (mats[i].w.layout != LAYOUT_TC) return false;
+        if (mats[i].w.layout != LAYOUT_TC || !gemm_tc_supported(mats[i].w)) return false;
     return M >= 1 && M <= GEMV_MTOK;
 }
 
@@ -576,73 +68,16 @@ int gemv_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, c
     EXL2B_REQUIRE(nm >= 1 && nm <= GEMV_MAX_MATS, "bad matrix count %d", nm);
     EXL2B_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
     if (M <= 0) return 0;
-    if (mats[0].w.layout == LAYOUT_TC) return gemm_tc_launch(device, stream, mats, nm, M, norm_w, norm_eps, epilogue, ex);
-    EXL2B_REQUIRE(!ex, "epilogue fusions are only implemented for the tcgen05 layout");
-    DeviceWorkspace* dw = nullptr;
-    int rc = ensure_workspace(device, &dw);
-    if (rc) return rc;
+    for (int i = 0; i < nm; ++i) EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_TC, "matrix is not in the default (tcgen05) layout");
+    return gemm_tc_launch(device, stream, mats, nm, M, norm_w, norm_eps, epilogue, ex);
+}
 
-    GemvParams P = {};
-    P.num_mats = nm;
-    P.KS = mats[0].w.KS;
-    long long units = 0;
-    int strips = 0;
-    for (int i = 0; i < nm; ++i) {
-        EXL2B_REQUIRE(mats[i].w.KS == P.KS, "fused matrices must share K");
-        EXL2B_REQUIRE(mats[i].w.layout == LAYOUT_MMA, "matrix is not in the mma.sync layout");
-        P.mat[i] = mats[i];
-        P.mat[i].unit_begin = (int)units;
-        P.mat[i].strip_begin = strips;
-        units += (long long)mats[i].w.strips * P.KS;
-        strips += mats[i].w.strips;
-    }
-    if (norm_w) EXL2B_REQUIRE(mats[0].w.K % 8 == 0 && mats[0].ldx % 8 == 0, "fused RMSNorm needs K and the row stride to be multiples of 8");
-    if (epilogue != EPI_STORE)
-        EXL2B_REQUIRE(nm == 2 && mats[0].w.N == mats[1].w.N, "gate/up epilogue needs two matrices of equal width");
-    P.norm_w = norm_w;
-    P.norm_eps = norm_eps;
-    P.epilogue = epilogue;
-    P.ws = dw->ws;
-    P.counters = dw->counters;
-    P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
-    P.dbg_cta = g_dbg_cta;
-
-    const int sms = device_sm_count(device);
-    // Grid: when every strip can be cut into S equal K-ranges with strips * S <= resident slots, do exactly that
-    // (every CTA = one segment of one strip, no CTA pays the per-segment latency chain twice); otherwise plain
-    // stream-K over all slots.
-    const long long slots = (long long)sms * g_ctas_per_sm;
-    long long grid_ll = std::min(slots, units);
-    if (strips <= slots) {
-        int S = (int)(slots / strips);
-        while (S > 1 && (P.KS % S) != 0) --S;
-        grid_ll = (long long)strips * S;
-    }
-    const int grid = (int)std::max(1ll, grid_ll);
-    EXL2B_REQUIRE((units + 1) * grid < (1ll << 31), "problem too large for 32-bit unit arithmetic");
-    P.total_units = (int)units;
-    const int seg_max = (int)std::min((long long)P.KS, (units + grid - 1) / grid);
-    P.act_rows = seg_max * SLAB_K;
-    P.act_stride = ((P.act_rows * 2 + 127) / 128) * 128 + 64;
-    P.maxc = (int)(((long long)P.KS * grid) / units) + 2;
-    EXL2B_REQUIRE(strips <= dw->n_counters, "too many strips for the counter array");
-    EXL2B_REQUIRE((size_t)strips * P.maxc * RED_FLOATS * sizeof(float) <= dw->ws_bytes, "split-K workspace too small");
-
-    const int fixed = SMEM_RINGS + SMEM_BARS + SMEM_MISC;
-    const int per_tok = P.act_stride + GEMV_WARPS * STRIP_N * 4;        // staged activations + reduction scratch
-    int tok_per_pass = std::min(GEMV_MTOK, (227 * 1024 - fixed) / per_tok);
-    EXL2B_REQUIRE(tok_per_pass >= 1, "K too large to stage one activation row (%d bytes)", P.act_stride);
-
-    for (int m0 = 0; m0 < M; m0 += tok_per_pass) {
-        P.M = std::min(tok_per_pass, M - m0);
-        for (int i = 0; i < nm; ++i) {
-            P.mat[i].x = mats[i].x + (size_t)m0 * mats[i].ldx;
-            P.mat[i].c = mats[i].c + (size_t)m0 * mats[i].ldc;
-        }
-        const size_t smem = (size_t)fixed + (size_t)P.M * per_tok;
-        EXL2B_CUDA(launch_pdl(gemv_kernel, dim3(grid), dim3(GEMV_THREADS), smem, stream, P));
-    }
-    return 0;
+// The tcgen05 kernel stages one quantisation group of a 32-column block per ring slot (<= 4 KB): groups of 256+ rows above 4
+// bits, or ungrouped GPTQ, do not fit.  Such matrices take the dense path for every row count above one.
+bool gemm_tc_supported(const QMatView& v) {
+    for (int r = 0; r < v.num_regions; ++r)
+        if ((1 << v.reg[r].spg_log2) * block_bytes(v.reg[r].bits) > 4096) return false;
+    return true;
 }
 
 }  // namespace exl2b
@@ -661,7 +96,7 @@ extern "C" int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int 
         const I8Input in = {(const half*)a, nullptr, nullptr, 0.f, I8_PLAIN};
         return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
     }
-    if (m > GEMM_BIG_MIN_ROWS && gemm_big_available())      // prefill rows: reconstruct + tensor-core GEMM (q_gemm.cu:233-266)
+    if ((m > GEMM_BIG_MIN_ROWS || !gemm_tc_supported(q->v)) && gemm_big_available())      // prefill rows: reconstruct + tensor-core GEMM (q_gemm.cu:233-266)
         return gemm_big_launch(q, (const half*)a, lda, (half*)c, ldc, m, clear ? 1 : 0, (cudaStream_t)stream);
     GemvMat mt = {};
     mt.w = q->v;

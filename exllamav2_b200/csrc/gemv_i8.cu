@@ -31,8 +31,7 @@
 
 namespace exl2b {
 
-constexpr int I8_WARPS = 16;
-constexpr int I8_THREADS = I8_WARPS * 32;
+constexpr int I8_MAX_WARPS = 16;
 constexpr int I8_MAX_STAGES = 4;
 constexpr int I8_MAX_CTAS = 160;
 constexpr int I8_SLOT_BYTES = 2048;       // one stage: 4 slabs (128 k) at <= 4 bits, 2 slabs above
@@ -84,19 +83,17 @@ __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
 // That is the byte order (w & 0x0f0f0f0f) / (w & 0xf0f0f0f0) of a 4-bit plane word has (layout.h: field e of pair slot j
 // at bit 16e + 4j, k = 8w + 2j + e); other planes reach their order with one PRMT per operand.
 template <int BITS>
-__device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, const uint8_t* __restrict__ xs, int lane,
-                                             int (&am)[4], int (&ae)[2]) {
+__device__ __forceinline__ void consume_slab(uint32_t wb, uint32_t xs, int lane, int (&am)[4], int (&ae)[2]) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
     uint32_t XH[8], XL[8];
     {
-        const uint4* xp = reinterpret_cast<const uint4*>(xs);
-        const uint4 h0 = xp[0], h1 = xp[1], l0 = xp[2], l1 = xp[3];
+        const uint4 h0 = lds128(xs), h1 = lds128(xs + 16), l0 = lds128(xs + 32), l1 = lds128(xs + 48);
         XH[0] = h0.x; XH[1] = h0.y; XH[2] = h0.z; XH[3] = h0.w; XH[4] = h1.x; XH[5] = h1.y; XH[6] = h1.z; XH[7] = h1.w;
         XL[0] = l0.x; XL[1] = l0.y; XL[2] = l0.z; XL[3] = l0.w; XL[4] = l1.x; XL[5] = l1.y; XL[6] = l1.z; XL[7] = l1.w;
     }
     // ---- main plane
     if constexpr (Pm == 4) {
-        const uint4 w4 = reinterpret_cast<const uint4*>(wb)[lane];
+        const uint4 w4 = lds128(wb + lane * 16);
         const uint32_t W[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -108,8 +105,7 @@ __device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, con
         }
     } else if constexpr (Pm == 8) {
         // word w: bytes = k 4w + {0,2,1,3}
-        const uint4* wp = reinterpret_cast<const uint4*>(wb);
-        const uint4 a4 = wp[lane], b4 = wp[32 + lane];
+        const uint4 a4 = lds128(wb + lane * 16), b4 = lds128(wb + 512 + lane * 16);
         const uint32_t W[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
@@ -119,7 +115,7 @@ __device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, con
             am[1] = dp4a_uu(W[w], __byte_perm(XL[2 * j], XL[2 * j + 1], sel), am[1]);
         }
     } else {   // Pm == 2: word w covers k = 16w .. 16w+15; field i of a byte: k 16w + {2i, 8+2i, 2i+1, 9+2i}
-        const uint2 w2 = reinterpret_cast<const uint2*>(wb)[lane];
+        const uint2 w2 = lds64(wb + lane * 8);
         const uint32_t W[2] = {w2.x, w2.y};
 #pragma unroll
         for (int w = 0; w < 2; ++w)
@@ -134,7 +130,7 @@ __device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, con
     }
     // ---- extra plane (bits above the main plane), at byte 128 * Pm of the block
     if constexpr (Pe == 1) {   // one word: bit i of a byte: k = {2i, 16+2i, 2i+1, 17+2i}
-        const uint32_t w = reinterpret_cast<const uint32_t*>(wb + 128 * Pm)[lane];
+        const uint32_t w = lds32(wb + 128 * Pm + lane * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int oa = i >> 2, ob = 2 + (i >> 2), t4 = i & 3, hi = t4 & 1;
@@ -144,7 +140,7 @@ __device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, con
             ae[1] = dp4a_uu(t, __byte_perm(XL[2 * oa + hi], XL[2 * ob + hi], sel), ae[1]);
         }
     } else if constexpr (Pe == 2) {
-        const uint2 w2 = reinterpret_cast<const uint2*>(wb + 128 * Pm)[lane];
+        const uint2 w2 = lds64(wb + 128 * Pm + lane * 8);
         const uint32_t W[2] = {w2.x, w2.y};
 #pragma unroll
         for (int w = 0; w < 2; ++w)
@@ -160,14 +156,13 @@ __device__ __forceinline__ void consume_slab(const uint8_t* __restrict__ wb, con
 }
 
 template <int BITS>
-__device__ __forceinline__ int consume_stage(const uint8_t* __restrict__ slot, int n, const uint8_t* __restrict__ xs,
-                                             const int* __restrict__ asum, int lane, int (&am)[4], int (&ae)[2]) {
-    constexpr int bb = 128 * BITS;
+__device__ __forceinline__ int consume_stage(uint32_t slot, int n, uint32_t xs, uint32_t asum, int lane, int (&am)[4], int (&ae)[2]) {
+    constexpr uint32_t bb = 128 * BITS;
     int S = 0;
 #pragma unroll 2
     for (int s = 0; s < n; ++s) {
         consume_slab<BITS>(slot + s * bb, xs + s * 64, lane, am, ae);
-        S += asum[s];
+        S += (int)lds32(asum + s * 4);
     }
     return S;
 }
@@ -237,7 +232,9 @@ __device__ __forceinline__ unsigned long long i8_gtimer() {
 #define I8_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && tid == 0) P.dbg[i] = i8_gtimer(); if ((i) == 0 && tid == 0) atomicMin(P.dbg + 6, i8_gtimer()); } } while (0)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_constant__ I8Params P) {
+template <int I8_WARPS>
+__global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_constant__ I8Params P) {
+    constexpr int I8_THREADS = I8_WARPS * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[I8_WARPS * I8_MAX_STAGES];
     __shared__ int4 descs[I8_WARPS * I8_MAX_STAGES];       // stage descriptors: written at issue, read at consumption
@@ -259,14 +256,15 @@ __global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_con
     const int units = nb * KS;
     const int l0 = (units * warp) / I8_WARPS, l1 = (units * (warp + 1)) / I8_WARPS;
 
-    uint8_t* const ring_g = smem + (size_t)warp * (size_t)(ns * I8_SLOT_BYTES);
-    const uint32_t ring = smem_addr(ring_g);
+    const uint32_t ring = smem_addr(smem) + (uint32_t)warp * (uint32_t)(ns * I8_SLOT_BYTES);
     const uint32_t bar0 = smem_addr(&bars[warp * I8_MAX_STAGES]);
-    int4* const my_descs = descs + warp * I8_MAX_STAGES;
+    const uint32_t desc0 = smem_addr(&descs[warp * I8_MAX_STAGES]);
+    int4* const my_descs = descs + warp * I8_MAX_STAGES;      // (written through the generic pointer by lane 0 at issue time)
     uint8_t* const act_g = smem + (size_t)I8_WARPS * (size_t)(ns * I8_SLOT_BYTES);      // staged row: [KS][64 B]
     int* const asum_s = reinterpret_cast<int*>(act_g + (size_t)KS * 64);                // [KS] integer sum of a slab's row values
     float* const ascale_s = reinterpret_cast<float*>(asum_s + KS);                      // [KS/4 + 1] scale of a 128-k block
     float* const emit_base = ascale_s + (KS / 4 + 1);                                   // [warp][2][32]
+    const uint32_t act = smem_addr(act_g), asum = smem_addr(asum_s), ascale = smem_addr(ascale_s);
 
     // ---- issue cursor: (block i_b relative to blk0, slab i_ks), matrix i_mi and its current region cached in registers
     int i_lin = l0, i_b = l0 / KS, i_ks = l0 - (l0 / KS) * KS, i_mi = 0, i_r = 0, islot = 0;
@@ -327,8 +325,8 @@ __global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_con
     __syncwarp();
     RawScale raw = {0u, __ushort_as_half(0)};
     if (l0 < l1) {
-        const int4 d0 = my_descs[0];
-        raw = load_scales(P, d0.w >> 24, d0.w & 0xffffff, d0.z, lane);
+        const uint4 d0 = lds128(desc0);
+        raw = load_scales(P, (int)(d0.w >> 24), (int)(d0.w & 0xffffffu), (int)d0.z, lane);
     }
 
     // ---- static operands of the prologue, fetched before the dependency wait: permutation indices (when the row has to be
@@ -477,17 +475,17 @@ __global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_con
     while (c_lin < l1) {
         mbar_wait(bar0 + cslot * 8, (phase >> cslot) & 1u);
         phase ^= 1u << cslot;
-        const int4 d = my_descs[cslot];
-        const int n = d.x & 0xff, bits = (d.x >> 8) & 0xff, flags = d.x >> 16, ks = d.y;
-        const uint8_t* slot = ring_g + (size_t)cslot * I8_SLOT_BYTES;
-        const uint8_t* xs = act_g + (size_t)ks * 64;
+        const uint4 d = lds128(desc0 + cslot * 16);
+        const int n = d.x & 0xff, bits = (d.x >> 8) & 0xff, flags = d.x >> 16, ks = (int)d.y;
+        const uint32_t slot = ring + (uint32_t)cslot * I8_SLOT_BYTES;
+        const uint32_t xs = act + (uint32_t)ks * 64u, as = asum + (uint32_t)ks * 4u;
         switch (bits) {
-            case 4: S += consume_stage<4>(slot, n, xs, asum_s + ks, lane, am, ae); break;
-            case 5: S += consume_stage<5>(slot, n, xs, asum_s + ks, lane, am, ae); break;
-            case 6: S += consume_stage<6>(slot, n, xs, asum_s + ks, lane, am, ae); break;
-            case 3: S += consume_stage<3>(slot, n, xs, asum_s + ks, lane, am, ae); break;
-            case 8: S += consume_stage<8>(slot, n, xs, asum_s + ks, lane, am, ae); break;
-            default: S += consume_stage<2>(slot, n, xs, asum_s + ks, lane, am, ae); break;
+            case 4: S += consume_stage<4>(slot, n, xs, as, lane, am, ae); break;
+            case 5: S += consume_stage<5>(slot, n, xs, as, lane, am, ae); break;
+            case 6: S += consume_stage<6>(slot, n, xs, as, lane, am, ae); break;
+            case 3: S += consume_stage<3>(slot, n, xs, as, lane, am, ae); break;
+            case 8: S += consume_stage<8>(slot, n, xs, as, lane, am, ae); break;
+            default: S += consume_stage<2>(slot, n, xs, as, lane, am, ae); break;
         }
         __syncwarp();
         if (i_lin < l1) issue_one();            // refill the slot just drained (islot == cslot here)
@@ -497,7 +495,7 @@ __global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_con
         cslot = (cslot + 1 == ns) ? 0 : cslot + 1;
         if (flags & DF_FLUSH) {
             // integer sums -> fp32:  sum_k a_k (q_k - zero) * scale  =  (sum a q - zero * sum a) * scale_w * scale_row
-            const int mi = d.w >> 24, blk = d.w & 0xffffff;
+            const int mi = (int)(d.w >> 24), blk = (int)(d.w & 0xffffffu);
             const I8Mat& m = P.mat[mi];
             const int col = (blk - m.blk_base) * 32 + lane;
             int v = ((am[0] << 8) + am[1]) + (((am[2] << 8) + am[3]) >> 4) + (((ae[0] << 8) + ae[1]) << plane_main(bits));
@@ -513,13 +511,13 @@ __global__ void __launch_bounds__(I8_THREADS, 2) gemv_i8_kernel(const __grid_con
                 zero = (int)nib + 1;                                                 // q_gemm_kernel_gptq.cuh:167-172
             }
             v -= zero * S;
-            tot = fmaf((float)v, ws * ascale_s[ks >> 2], tot);
+            tot = fmaf((float)v, ws * __uint_as_float(lds32(ascale + (uint32_t)(ks >> 2) * 4u)), tot);
             am[0] = am[1] = am[2] = am[3] = 0;
             ae[0] = ae[1] = 0;
             S = 0;
             if (c_lin < l1) {                  // scales of the next segment (its descriptor is already in the ring)
-                const int4 dn = my_descs[cslot];
-                raw = load_scales(P, dn.w >> 24, dn.w & 0xffffff, dn.z, lane);
+                const uint4 dn = lds128(desc0 + cslot * 16);
+                raw = load_scales(P, (int)(dn.w >> 24), (int)(dn.w & 0xffffffu), (int)dn.z, lane);
             }
             if (flags & DF_BLOCK_DONE) {
                 if (blk_slabs == KS) {
@@ -623,9 +621,17 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     EXL2B_REQUIRE(in.x, "null input row");
     EXL2B_REQUIRE(in.mode != I8_RMSNORM || in.norm_w, "RMSNorm prologue without a weight");
     EXL2B_REQUIRE((in.mode != I8_SILU_MUL && in.mode != I8_GELU_MUL) || in.x2, "act*mul prologue without the second operand");
+    // warps per CTA: 16 (64 registers / thread) or 12 (80) -- EXL2B_I8_WARPS selects, both keep two CTAs per SM resident
+    static const int warps = [] {
+        const char* e = getenv("EXL2B_I8_WARPS");
+        const int w = e ? atoi(e) : 16;
+        return (w == 12 || w == 8) ? w : 16;
+    }();
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[device] = true;
     }
 
@@ -679,19 +685,21 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
 
     // shared memory: weight rings + staged row (64 B + sum per slab, scale per 128 k) + per-warp partials
     const size_t act_bytes = (size_t)P.KS * 64 + (size_t)P.KS * 4 + (size_t)(P.KS / 4 + 1) * 4;
-    const size_t emit_bytes = (size_t)I8_WARPS * 2 * 32 * sizeof(float);
-    auto smem_for = [&](int ns) { return (size_t)I8_WARPS * ns * I8_SLOT_BYTES + act_bytes + emit_bytes; };
-    // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: stay <= 112 KB
-    // if a 2-slot ring achieves it
-    P.ns = 3;
-    if (smem_for(3) > 112 * 1024) P.ns = 2;
+    const size_t emit_bytes = (size_t)warps * 2 * 32 * sizeof(float);
+    auto smem_for = [&](int ns) { return (size_t)warps * ns * I8_SLOT_BYTES + act_bytes + emit_bytes; };
+    // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: the deepest ring
+    // (<= 4 slots per warp) that keeps the CTA <= 112 KB, never fewer than 2 slots
+    P.ns = I8_MAX_STAGES;
+    while (P.ns > 2 && smem_for(P.ns) > 112 * 1024) --P.ns;
     const size_t smem_total = smem_for(P.ns);
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes, K = %d)", smem_total, P.K);
     extern unsigned long long* g_dbg;
     extern int g_dbg_cta, g_dbg_slot;
     P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
-    EXL2B_CUDA(launch_pdl(gemv_i8_kernel, dim3(C), dim3(I8_THREADS), smem_total, stream, P));
+    if (warps == 16) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
+    else if (warps == 12) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
+    else EXL2B_CUDA(launch_pdl(gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
     return 0;
 }
 

@@ -1,26 +1,27 @@
-// Private HBM layout of a quantized matrix and the register-level unpack -- shared by the repack kernel, the
-// GEMV / GEMM kernels, reconstruct, and the host-side emulation in tests/emu (compiled with g++).
+// Private HBM layout of a quantized matrix and the register-level unpack -- shared by the repack kernel, the GEMV / GEMM
+// kernels, reconstruct, and the host-side emulation in tests/emu (compiled with g++).
 //
-// The reference keeps the checkpoint's [packed-row, column] order and re-shuffles bit fields inside each
-// 32-row column unit at load time (exllamav2_ext/cuda/q_matrix.cu:21-44, quant/qdq_*.cuh shuffle_*).  We do a
-// different load-time re-pack (same total bytes, written back over q_weight exactly like the reference mutates
-// it) into a layout built for B200 streaming:
+// The reference keeps the checkpoint's [packed-row, column] order and re-shuffles bit fields inside each 32-row column unit at
+// load time (exllamav2_ext/cuda/q_matrix.cu:21-44, quant/qdq_*.cuh shuffle_*).  We do a different load-time re-pack (same
+// total bytes, written back over q_weight exactly like the reference mutates it) into a layout built for B200 streaming.
 //
-//   strip  = 64 output columns; a strip's data is ONE contiguous byte stream over K, so any (strip, k-range)
-//            is a contiguous range that a warp fetches with cp.async.bulk (TMA 1-D) into shared memory.
-//   slab   = 32 consecutive stored rows k' of one strip = 2 blocks.
-//   block  = 32 k x 32 n.  Lane l (g = l>>2, t = l&3) owns 32 values: n in {g, g+8, g+16, g+24},
-//            k in {8t..8t+7}, stored so that after unpacking, registers ARE mma.m16n8k16 A-fragments
-//            (weights = A operand, tokens = the N=8 dimension).
-//   plane  = a b-bit value is split into power-of-two bit planes (b = main + extra: 2=2, 3=2+1, 4=4, 5=4+1,
-//            6=4+2, 8=8) so that every field sits at a position where `(w >> sh) & mask | magic` is a valid
-//            fp16 (the 0x6400 trick generalised to every exponent), two values per 32-bit op.
+// THE layout every kernel uses (LAYOUT_TC below):
+//   strip  = 128 output columns = 4 blocks; block = 32 k x 32 n; every block's slabs (32 stored rows k' each) form their own
+//            contiguous byte stream over K: [strip][block][slab].  Any (block, k-range) is ONE contiguous byte range that a
+//            warp fetches with cp.async.bulk (TMA 1-D).  Mixed bit widths along K only change the slab stride of a region.
+//   lane l of a block owns column n = l and all 32 k of the slab: value i <-> k_local = i, pair p = i / 2 = (k, k+1).
+//   plane  = a b-bit value is split into power-of-two bit planes (b = main + extra: 2=2, 3=2+1, 4=4, 5=4+1, 6=4+2, 8=8) with
+//            field e of pair slot j at bit 16e + P*j of its word, so that
+//              * `(w >> sh) & mask | magic` is a valid fp16 pair (the 0x6400 trick generalised to every exponent): the tcgen05
+//                kernel writes it straight to tensor memory as one 32-bit TMEM column of row n (gemm_tc.cu);
+//              * `w & 0x0f0f0f0f` / `w & 0xf0f0f0f0` (and the 2- / 1-bit analogues) are four BYTE operands of the integer
+//                dot-product instruction: the batch-1 GEMV feeds packed words to dp4a unexpanded (gemv_i8.cu).
 //
-// Value index inside a lane's 32 values:  i = p*2 + e,  pair p = sub*8 + s*4 + reg,  reg = h*2 + rr
-//   n_local = sub*16 + rr*8 + g          (sub: 16-column subtile, rr: row g / g+8 of the mma tile)
-//   k_local = 8t + 4s + 2h + e           (s: mma k-step, h: column half, e: element of the half2)
-// mma A registers of (sub, s):  A[reg] = half2(value e=0, value e=1).  The matching B fragment of step s is
-//   B0 = act[8t+4s+{0,1}],  B1 = act[8t+4s+{2,3}]  -> one 16-byte load of act[8t..8t+7] feeds both steps.
+// The round-1 mma.sync fragment layout (LAYOUT_MMA: strip = 64 columns, lane (g, t) owns n in {g, g+8, g+16, g+24} and
+// k in {8t..8t+7}) is no longer produced by the library; its index algebra stays here because tests/emu checks the
+// compose / extract / unpack logic for both mappings.
+//   Value index inside a lane's 32 values (MMA mapping):  i = p*2 + e,  pair p = sub*8 + s*4 + reg,  reg = h*2 + rr
+//   n_local = sub*16 + rr*8 + g,  k_local = 8t + 4s + 2h + e
 #pragma once
 #include <stdint.h>
 

@@ -312,11 +312,7 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
     QMatrix* m = new QMatrix();
     m->device = d->device;
     QMatView& v = m->v;
-    static const int default_layout = [] {
-        const char* e = getenv("EXL2B_LAYOUT");
-        return (e && e[0] == 'm') ? LAYOUT_MMA : LAYOUT_TC;
-    }();
-    v.layout = default_layout;
+    v.layout = LAYOUT_TC;       // one layout serves every kernel (layout.h); the round-1 mma.sync layout is kept only as layout algebra
     v.K = d->height;
     v.N = d->width;
     v.KS = v.K / SLAB_K;

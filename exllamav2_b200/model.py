@@ -190,11 +190,12 @@ class ExLlamaV2Decoder:
         self.xn = torch.empty((B, hid), dtype=torch.half, device=dev)
         self.logits = torch.empty((B, cfg.vocab_size), dtype=torch.half, device=dev)
         self.graph = None
+        self.pos = 0        # host-side mirror of cache_seqlens (which lives on the device): bounds are checked BEFORE a launch
         # True: attention reads the Q4 cache directly (one kernel per layer); False: the reference's sequence
         # q_to_fp16_kv -> attention on the fp16 temp -> fp16_to_q_kv (three kernels + the temp round trip)
         self.fused_attn = os.environ.get("EXL2B_REF_KV_SEQUENCE") is None
         # producer epilogues feed consumer activation buffers (needs the default tcgen05 matrix layout)
-        self.chained = os.environ.get("EXL2B_NO_CHAIN") is None and not os.environ.get("EXL2B_LAYOUT", "").startswith("m")
+        self.chained = os.environ.get("EXL2B_NO_CHAIN") is None
         # single rows (bs = 1 decode) run on the HBM-bound integer GEMV (csrc/gemv_i8.cu) in the reference's own op sequence
         self.row_gemv = os.environ.get("EXL2B_GEMV", "")[:1] != "t"
         for L in self.layers:
@@ -293,6 +294,9 @@ class ExLlamaV2Decoder:
 
     def decode(self, ids: torch.Tensor) -> torch.Tensor:
         """ids [B, 1] (device) -> logits fp16 [B, vocab]; advances the cache by one token."""
+        if self.pos + 1 > self.cache.max_seq_len:
+            raise RuntimeError(f"K/V cache is full ({self.pos} of {self.cache.max_seq_len} positions): decode would run past the page table")
+        self.pos += 1
         self.ids.copy_(ids)
         if self.graph is not None:
             self.graph.replay()
@@ -306,6 +310,9 @@ class ExLlamaV2Decoder:
         B, T = ids.shape
         cfg = self.cfg
         H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        if self.pos + T > self.cache.max_seq_len:
+            raise RuntimeError(f"prompt of {T} tokens does not fit the K/V cache ({self.pos} of {self.cache.max_seq_len} positions used)")
+        self.pos += T
         for t0 in range(0, T, chunk):
             n = min(chunk, T - t0)
             x = self.embed[ids[:, t0:t0 + n]].contiguous()

@@ -129,9 +129,9 @@ class ExLlamaV2DecoderTP:
         self.weight_bytes = 0
         self.layers, self.linears = [], []
 
-        def lin(K, N, plan, s, cols):
+        def lin(K, N, plan, s, cols, perm_seed=None):
             bits, prop, gs = plan
-            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K))
+            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
             a, b = cols
             ws = tp_column_slice_t(w, a, b)
             del w
@@ -148,17 +148,19 @@ class ExLlamaV2DecoderTP:
         for li in range(cfg.num_layers):
             L = _L()
             mp = cfg.plan.mlp[li % len(cfg.plan.mlp)]
-            L.q_proj = lin(hid, H * hd, cfg.plan.attn, s + 1, tp.mine(tp.q))
-            L.k_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 2, tp.mine(tp.kv))
-            L.v_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 3, tp.mine(tp.kv))
+            # same tensors as model.ExLlamaV2Decoder (k / v share q's permutation, up shares gate's)
+            L.q_proj = lin(hid, H * hd, cfg.plan.attn, s + 1, tp.mine(tp.q), s + 1)
+            L.k_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 2, tp.mine(tp.kv), s + 1)
+            L.v_proj = lin(hid, KVH * hd, cfg.plan.attn, s + 3, tp.mine(tp.kv), s + 1)
             L.o_proj = lin(H * hd, hid, cfg.plan.attn, s + 4, tp.mine(tp.rs))
-            L.gate = lin(hid, inter, mp, s + 5, tp.mine(tp.id))
-            L.up = lin(hid, inter, mp, s + 6, tp.mine(tp.id))
+            L.gate = lin(hid, inter, mp, s + 5, tp.mine(tp.id), s + 5)
+            L.up = lin(hid, inter, mp, s + 6, tp.mine(tp.id), s + 5)
             L.down = lin(inter, hid, mp, s + 7, tp.mine(tp.rs))
             s += 16
             L.input_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
             L.post_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
             L.temp_a = torch.empty((64, self.inter_l), dtype=torch.half, device=dev)
+            L.temp_b = torch.empty((64, self.inter_l), dtype=torch.half, device=dev)
             # rank-local blocks: this rank's heads / intermediate columns; o_proj and down are applied as column shards below
             L.attn = ext_c.make_q_attn(L.input_norm, none_tensor, True, False, cfg.norm_eps, L.q_proj.q_handle, L.k_proj.q_handle,
                                        L.v_proj.q_handle, 0, none_tensor, none_tensor, 64, hid, self.Hl, self.KVHl, hd,
@@ -185,6 +187,7 @@ class ExLlamaV2DecoderTP:
         self.xn = torch.empty((B, hid), dtype=torch.half, device=dev)
         self.logits = torch.empty((B, cfg.vocab_size), dtype=torch.half, device=dev)
         self.graph = None
+        self.pos = 0
 
     def _forward_rows(self, x, q, k, v, q_len: int):
         """x [rows, hidden] replicated on every rank; rows = B * q_len."""
@@ -228,6 +231,9 @@ class ExLlamaV2DecoderTP:
     def prefill(self, ids: torch.Tensor, chunk: int = 8):
         B, T = ids.shape
         hd = self.cfg.head_dim
+        if self.pos + T > self.cache.max_seq_len:
+            raise RuntimeError(f"prompt of {T} tokens does not fit the K/V cache")
+        self.pos += T
         for t0 in range(0, T, chunk):
             n = min(chunk, T - t0)
             x = self.embed[ids[:, t0:t0 + n]].reshape(B * n, -1).contiguous()
@@ -252,6 +258,9 @@ class ExLlamaV2DecoderTP:
         return g
 
     def decode(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.pos + 1 > self.cache.max_seq_len:
+            raise RuntimeError(f"K/V cache is full ({self.pos} of {self.cache.max_seq_len} positions)")
+        self.pos += 1
         self.ids.copy_(ids)
         if self.graph is not None:
             self.graph.replay()
