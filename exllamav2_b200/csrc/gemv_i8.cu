@@ -691,6 +691,8 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     // (<= 4 slots per warp) that keeps the CTA <= 112 KB, never fewer than 2 slots
     P.ns = I8_MAX_STAGES;
     while (P.ns > 2 && smem_for(P.ns) > 112 * 1024) --P.ns;
+    static const int ns_override = [] { const char* e = getenv("EXL2B_I8_NS"); return e ? atoi(e) : 0; }();     // tuning knob
+    if (ns_override >= 2 && ns_override <= I8_MAX_STAGES) P.ns = ns_override;
     const size_t smem_total = smem_for(P.ns);
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes, K = %d)", smem_total, P.K);
     extern unsigned long long* g_dbg;

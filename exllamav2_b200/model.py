@@ -66,6 +66,9 @@ def _mix_4bpw() -> QuantPlan:
 PRESETS = {
     "llama2-7b-4.0bpw": lambda: LlamaConfig("llama2-7b-4.0bpw", 4096, 11008, 32, 32, 128, 32, 32000, plan=_mix_4bpw()),
     "llama2-7b-4bit-g128": lambda: LlamaConfig("llama2-7b-4bit-g128", 4096, 11008, 32, 32, 128, 32, 32000),
+    # BASELINE config 4: GPTQ 4-bit, group 128, act-order (q/k/v and gate/up share g_idx)
+    "llama2-7b-gptq-g128-act": lambda: LlamaConfig("llama2-7b-gptq-g128-act", 4096, 11008, 32, 32, 128, 32, 32000,
+                                                    plan=QuantPlan(attn=("gptq", 128, True), mlp=[("gptq", 128, True)], head=((6,), (1.0,), 128))),
     "tinyllama-1.1b-4.0bpw": lambda: LlamaConfig("tinyllama-1.1b-4.0bpw", 2048, 5632, 32, 4, 64, 22, 32000),
     "llama2-70b-2.5bpw": lambda: LlamaConfig(
         "llama2-70b-2.5bpw", 8192, 28672, 64, 8, 128, 80, 32000,
@@ -143,8 +146,7 @@ class ExLlamaV2Decoder:
         max_rows = 64
 
         def lin(K, N, plan, s, perm_seed=None):
-            bits, prop, gs = plan
-            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
+            w = synthetic.random_linear(K, N, plan, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
             self.weight_bytes += synthetic.algorithmic_bytes(w, 1)
             l = ExLlamaV2Linear(K, N, device=dev)
             l.load(w)

@@ -69,19 +69,34 @@ def random_exl2(K: int, N: int, bits=(4,), bits_prop=(1.0,), group_size=128, dev
     return w
 
 
-def random_gptq(K: int, N: int, group_size: int = 128, device="cuda:0", seed: int = 0, act_order: bool = False) -> dict:
+def random_gptq(K: int, N: int, group_size: int = 128, device="cuda:0", seed: int = 0, act_order: bool = False,
+                weight_std: float | None = None, perm_seed: int | None = None) -> dict:
+    """Random GPTQ 4-bit tensors.  weight_std: standard deviation of the dequantised weights (std of q - zero for uniform
+    nibbles is ~6.5); None: scales ~ U(0.002, 0.02) as in SURVEY.md 8d C1.  perm_seed: matrices quantised against the same
+    input share their act-order g_idx."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     G = K // group_size
     g_idx = (torch.arange(K) // group_size).to(torch.int32)
     if act_order:
-        g_idx = g_idx[torch.randperm(K, generator=torch.Generator().manual_seed(seed))]
+        g_idx = g_idx[torch.randperm(K, generator=torch.Generator().manual_seed(seed if perm_seed is None else 0x5EED0000 + perm_seed))]
+    scales = torch.rand((G, N), device=device, generator=gen) * 0.018 + 0.002
+    if weight_std is not None:
+        scales = scales * (weight_std / (0.011 * 6.5))
     return {
         "qweight": torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=device, generator=gen),
         "qzeros": torch.randint(-2**31, 2**31 - 1, (G, N // 8), dtype=torch.int32, device=device, generator=gen),
-        "scales": (torch.rand((G, N), device=device, generator=gen) * 0.018 + 0.002).half(),
+        "scales": scales.half(),
         "g_idx": g_idx,
     }
+
+
+def random_linear(K: int, N: int, plan, device="cuda:0", seed: int = 0, weight_std: float | None = None, perm_seed: int | None = None) -> dict:
+    """plan = (bits, bits_prop, group_size) for EXL2, or ("gptq", group_size, act_order)."""
+    if plan[0] == "gptq":
+        return random_gptq(K, N, plan[1], device, seed, act_order=plan[2], weight_std=weight_std, perm_seed=perm_seed)
+    bits, prop, gs = plan
+    return random_exl2(K, N, bits, prop, gs, device=device, seed=seed, weight_std=weight_std, perm_seed=perm_seed)
 
 
 def algorithmic_bytes(w: dict, M: int = 1, accumulate: bool = False) -> int:
@@ -92,6 +107,6 @@ def algorithmic_bytes(w: dict, M: int = 1, accumulate: bool = False) -> int:
     else:
         K, N = w["qweight"].shape[0] * 8, w["qweight"].shape[1]
         b = w["qweight"].numel() * 4 + w["qzeros"].numel() * 4 + w["scales"].numel() * 2
-        if "q_perm" in w:
+        if "q_perm" in w or ("g_idx" in w and not bool((w["g_idx"][:-1] <= w["g_idx"][1:]).all())):
             b += 2 * K
     return b + 2 * M * K + 2 * M * N * (2 if accumulate else 1)

@@ -130,8 +130,7 @@ class ExLlamaV2DecoderTP:
         self.layers, self.linears = [], []
 
         def lin(K, N, plan, s, cols, perm_seed=None):
-            bits, prop, gs = plan
-            w = synthetic.random_exl2(K, N, bits, prop, gs, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
+            w = synthetic.random_linear(K, N, plan, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
             a, b = cols
             ws = tp_column_slice_t(w, a, b)
             del w
