@@ -448,6 +448,15 @@ def make_q_mlp(layernorm, layernorm_bias, layernorm_is_rms: bool, norm_epsilon: 
 _mlp_temps: dict[int, tuple] = {}
 
 
+def q_mlp_forward_rows(q_mlp: int, x, temp_a, temp_b):
+    """q_mlp_forward_ with caller-provided scratch rows (the reference sizes temp_a / temp_b for max_input_len at make_q_mlp
+    time, mlp.py:176-203; a prompt chunk larger than that brings its own)."""
+    _cuda(x, "x")
+    _dtype(x, torch.float16, "x")
+    rows = x.numel() // x.shape[-1]
+    _check(lib.exl2b_qmlp_forward(q_mlp, x.data_ptr(), rows, temp_a.data_ptr(), temp_b.data_ptr(), _stream(x)))
+
+
 def free_q_mlp(handle: int):
     _mlp_temps.pop(handle, None)
     _check(lib.exl2b_qmlp_destroy(handle))

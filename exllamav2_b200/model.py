@@ -127,6 +127,53 @@ class ExLlamaV2Cache_Q4:
         return sum(t.numel() * t.element_size() for ts in (self.key_states, self.value_states, self.key_scales, self.value_scales) for t in ts)
 
 
+_FA = [False, None]
+
+
+def _flash_attn_with_kvcache():
+    """flash_attn_with_kvcache if flash-attn imports AND runs on this GPU, else None (probed once)."""
+    if not _FA[0]:
+        _FA[0] = True
+        try:
+            from flash_attn import flash_attn_with_kvcache
+            dev = torch.device("cuda")
+            qq = torch.zeros((1, 1, 1, 64), dtype=torch.half, device=dev)
+            kc = torch.zeros((1, 256, 1, 64), dtype=torch.half, device=dev)
+            flash_attn_with_kvcache(q=qq, k=qq.clone(), v=qq.clone(), k_cache=kc, v_cache=kc.clone(),
+                                    cache_seqlens=torch.zeros((1,), dtype=torch.int32, device=dev),
+                                    block_table=torch.zeros((1, 1), dtype=torch.int32, device=dev), causal=True)
+            torch.cuda.synchronize()
+            _FA[1] = flash_attn_with_kvcache
+        except Exception:      # noqa: BLE001
+            _FA[1] = None
+    return _FA[1]
+
+
+def _sdpa_prefill(q, k, v, tk, tv, cache, hd):
+    """Causal attention of a prompt chunk over the paged fp16 temp cache with torch SDPA (per sequence; identity-free page walk)."""
+    B, T, H, _ = q.shape
+    KVH = k.shape[2]
+    outs = []
+    seqlens = cache.cache_seqlens.tolist()
+    for b in range(B):
+        n0 = int(seqlens[b])
+        pages = cache.block_table[b].long()
+        kc = tk[pages].reshape(-1, KVH, hd)
+        vc = tv[pages].reshape(-1, KVH, hd)
+        kc[n0:n0 + T] = k[b]
+        vc[n0:n0 + T] = v[b]
+        tk[pages] = kc.view(-1, tk.shape[1], KVH, hd)
+        tv[pages] = vc.view(-1, tv.shape[1], KVH, hd)
+        kk = kc[: n0 + T].transpose(0, 1)
+        vv = vc[: n0 + T].transpose(0, 1)
+        if H != KVH:
+            kk, vv = kk.repeat_interleave(H // KVH, dim=0), vv.repeat_interleave(H // KVH, dim=0)
+        mask = torch.ones((T, n0 + T), dtype=torch.bool, device=q.device).tril(diagonal=n0)
+        o = torch.nn.functional.scaled_dot_product_attention(q[b].transpose(0, 1), kk, vv, attn_mask=mask)
+        outs.append(o.transpose(0, 1))
+    return torch.stack(outs)
+
+
 class _Layer:
     pass
 
@@ -323,6 +370,37 @@ class ExLlamaV2Decoder:
             v = torch.empty_like(k)
             ao = torch.empty_like(q)
             self._forward_tokens(x, q, k, v, ao, n)
+        return x
+
+    def prefill_rows(self, ids: torch.Tensor):
+        """Whole prompt [B, T] in ONE pass per matrix (the many-row path, csrc/gemm_big.cu), in the reference's own op sequence for
+        a prompt chunk (attn.py:466-638): get_kv_state -> q_attn_forward_1 -> flash_attn_with_kvcache on the fp16 temp (third-party
+        there too; torch SDPA when flash-attn does not run on this GPU) -> store_kv_state -> q_attn_forward_2 -> q_mlp_forward_."""
+        B, T = ids.shape
+        cfg, cache = self.cfg, self.cache
+        H, KVH, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        if self.pos + T > cache.max_seq_len:
+            raise RuntimeError(f"prompt of {T} tokens does not fit the K/V cache")
+        self.pos += T
+        x = self.embed[ids].contiguous()
+        q = torch.empty((B, T, H * hd), dtype=torch.half, device=self.device)
+        k = torch.empty((B, T, KVH * hd), dtype=torch.half, device=self.device)
+        v = torch.empty_like(k)
+        ta = torch.empty((B * T, cfg.intermediate_size), dtype=torch.half, device=self.device)
+        tb = torch.empty_like(ta)
+        fa = _flash_attn_with_kvcache()
+        for li, L in enumerate(self.layers):
+            tk, tv = cache.get_kv_state(li)
+            ext_c.q_attn_forward_1(L.attn, x, B, T, -1, cache.cache_seqlens, q, k, v, self.sin, self.cos)
+            if fa is not None:
+                ao = fa(q=q.view(B, T, H, hd), k=k.view(B, T, KVH, hd), v=v.view(B, T, KVH, hd), k_cache=tk, v_cache=tv,
+                        cache_seqlens=cache.cache_seqlens, block_table=cache.block_table, causal=True, softmax_scale=1.0 / math.sqrt(hd))
+            else:
+                ao = _sdpa_prefill(q.view(B, T, H, hd), k.view(B, T, KVH, hd), v.view(B, T, KVH, hd), tk, tv, cache, hd)
+            cache.store_kv_state(li, T)
+            ext_c.q_attn_forward_2(L.attn, x, ao.reshape(B, T, H * hd), B, T)
+            ext_c.q_mlp_forward_rows(L.mlp, x.view(B * T, -1), ta, tb)
+        cache.cache_seqlens.add_(T)
         return x
 
     def unload(self):
