@@ -74,8 +74,9 @@ bool gemm_big_available() {
 int gemm_big_launch(const QMatrix* q, const half* a, int lda, half* c, int ldc, int M, int clear, cudaStream_t stream) {
     const QMatView& v = q->v;
     cublasHandle_t h = nullptr;
+    // one cuBLAS handle per device: host-side use is serialised (the work itself is asynchronous on `stream`)
+    std::lock_guard<std::mutex> lk(g_cb_mutex);
     {
-        std::lock_guard<std::mutex> lk(g_cb_mutex);
         EXL2B_REQUIRE(cublas_load(), "cuBLAS is not loadable (libcublas.so.12): the many-row path is unavailable");
         const int d = q->device;
         EXL2B_REQUIRE(d >= 0 && d < 64, "bad device");

@@ -907,9 +907,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
 // ---- host launcher -----------------------------------------------------------------------------------------------------
 
-int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters);
+int gemv_workspace(int device, cudaStream_t stream, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters, half** xp,
+                   size_t xp_bytes);
 
-static half* g_xp_scratch[64] = {nullptr};
 constexpr size_t TC_XP_BYTES_PER_MAT = (size_t)65536 * 16;      // K <= 65536, 16 B per k (8 token slots)
 
 int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M, const half* norm_w, float norm_eps, int epilogue,
@@ -920,14 +920,14 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
     unsigned int* counters = nullptr;
     size_t ws_bytes = 0;
     int n_counters = 0;
-    int rc = gemv_workspace(device, &ws, &counters, &ws_bytes, &n_counters);
+    half* xp_scratch = nullptr;
+    int rc = gemv_workspace(device, stream, &ws, &counters, &ws_bytes, &n_counters, &xp_scratch, TC_XP_BYTES_PER_MAT * GEMV_MAX_MATS);
     if (rc) return rc;
-    static bool attr_set[64] = {false};
-    if (!attr_set[device]) {
+    static std::atomic<bool> attr_set[64];
+    if (!attr_set[device].load()) {
         EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         EXL2B_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        EXL2B_CUDA(cudaMalloc(&g_xp_scratch[device], TC_XP_BYTES_PER_MAT * GEMV_MAX_MATS));
-        attr_set[device] = true;
+        attr_set[device].store(true);
     }
 
     GemvParams P = {};
@@ -951,7 +951,7 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
         P.mat[i].unit_begin = (int)units;
         P.mat[i].strip_begin = strips;
         if (prepared) EXL2B_REQUIRE(mats[i].xp, "prepared launch without an activation buffer");
-        else P.mat[i].xp = g_xp_scratch[device] + (size_t)i * (TC_XP_BYTES_PER_MAT / sizeof(half));
+        else P.mat[i].xp = xp_scratch + (size_t)i * (TC_XP_BYTES_PER_MAT / sizeof(half));
         units += (long long)mats[i].w.strips * P.KS;
         strips += mats[i].w.strips;
     }

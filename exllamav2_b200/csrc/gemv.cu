@@ -4,6 +4,7 @@
 //   more         -> gemm_big.cu  (reconstruct window + dense tensor-core GEMM: the reference's regime above MAX_Q_GEMM_ROWS)
 // Replaces gemm_half_q_half_cuda (exllamav2_ext/cuda/q_gemm.cu:201-313).
 #include <algorithm>
+#include <map>
 #include <mutex>
 
 #include "gemv.cuh"
@@ -17,39 +18,41 @@ unsigned long long* g_dbg = nullptr;
 int g_dbg_cta = 0;
 int g_dbg_slot = 0;
 
-struct DeviceWorkspace {
+// Split-K workspace, arrival counters and the activation-operand scratch of the tcgen05 kernel, one set per (device, stream):
+// launches on different streams (or host threads driving different streams) never share scratch.  Created on first use --
+// never inside a stream capture: call once eagerly first, as model.capture() does.
+struct TcWorkspace {
     float* ws = nullptr;
     unsigned int* counters = nullptr;
-    size_t ws_bytes = 0;
+    half* xp = nullptr;
+    size_t ws_bytes = 0, xp_bytes = 0;
     int n_counters = 0;
-    bool attr_set = false;
 };
-static DeviceWorkspace g_ws[64];
+static std::map<std::pair<int, cudaStream_t>, TcWorkspace> g_tc_ws;
 static std::mutex g_ws_mutex;
 
-static int ensure_workspace(int device, DeviceWorkspace** out) {
+int gemv_workspace(int device, cudaStream_t stream, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters, half** xp,
+                   size_t xp_bytes) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
-    DeviceWorkspace& d = g_ws[device];
+    TcWorkspace& d = g_tc_ws[{device, stream}];
     if (!d.ws) {
-        d.ws_bytes = (size_t)64 << 20;
-        d.n_counters = 1 << 20;
+        d.ws_bytes = (size_t)32 << 20;
+        d.n_counters = 1 << 16;
         EXL2B_CUDA(cudaMalloc(&d.ws, d.ws_bytes));
         EXL2B_CUDA(cudaMalloc(&d.counters, d.n_counters * sizeof(unsigned int)));
         EXL2B_CUDA(cudaMemset(d.counters, 0, d.n_counters * sizeof(unsigned int)));
         EXL2B_CUDA(cudaDeviceSynchronize());
     }
-    *out = &d;
-    return 0;
-}
-
-int gemv_workspace(int device, float** ws, unsigned int** counters, size_t* ws_bytes, int* n_counters) {
-    DeviceWorkspace* dw = nullptr;
-    int rc = ensure_workspace(device, &dw);
-    if (rc) return rc;
-    *ws = dw->ws;
-    *counters = dw->counters;
-    *ws_bytes = dw->ws_bytes;
-    *n_counters = dw->n_counters;
+    if (d.xp_bytes < xp_bytes) {
+        if (d.xp) EXL2B_CUDA(cudaFree(d.xp));
+        EXL2B_CUDA(cudaMalloc(&d.xp, xp_bytes));
+        d.xp_bytes = xp_bytes;
+    }
+    *ws = d.ws;
+    *counters = d.counters;
+    *ws_bytes = d.ws_bytes;
+    *n_counters = d.n_counters;
+    *xp = d.xp;
     return 0;
 }
 
