@@ -32,7 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "decode tokens/sec (bs=1) Llama2-7B EXL2-4.0bpw"
+METRIC = "decode tokens/sec (bs=1) Llama2-7B EXL2-4.0bpw"       # the default --model; other presets are named in config.workload
 UNIT = "tokens/s"
 
 
@@ -374,7 +374,7 @@ def run_ours(args, rank, world):
                 "gemv_launches_per_token": n_gemv, "avg_launch_us": ms_gemv * 1e3 / n_gemv,
                 "note": f"{n_launch_roof} launches ({n_gemv} dequant-GEMMs + their prep/rope launches, if any) replayed back to back in one CUDA graph, CUDA events"}
 
-    cpu = cpu_port_baseline(args.model) if not args.no_cpu else None
+    cpu = cpu_port_baseline(args.model) if (not args.no_cpu and args.model in REF_ARM_CONFIGS) else None
     # ---- the real competitor: the unmodified reference extension (oracle/_ref) on the same synthetic model, same GPU, same
     #      process, in the reference's own per-layer op sequence (oracle/ref_decoder.py); outside every timed region of ours
     ref_ext = None
@@ -392,8 +392,8 @@ def run_ours(args, rank, world):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16 (int2-8 weights, fp32 accumulate)",
         "data": "synthetic",
         "config": {"workload": f"{cfg.name} single-stream decode, {args.prompt_len}-token prompt, Q4 KV cache, bs=1",
-                   "l2": "inputs_exceed_l2 (3.3 GB of weights per step)", "weight_bytes": dec.weight_bytes, "build_s": round(t_build, 1),
-                   "bpw_layers": "attn [5,4]@.1/.9 g128; mlp 3/4 layers [5,4], 1/4 [4,3]; head 6-bit"},
+                   "l2": f"inputs_exceed_l2 ({dec.weight_bytes / 1e9:.2f} GB of weights per step)", "weight_bytes": dec.weight_bytes, "build_s": round(t_build, 1),
+                   "quant_plan": {"attn": str(cfg.plan.attn), "mlp (cycled over layers)": str(cfg.plan.mlp), "head": str(cfg.plan.head)}},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "reference_cuda_ext": ref_ext,
     }

@@ -61,10 +61,29 @@ struct I8Params {
     float norm_eps;
     int mode, x_permuted;
     int ns;                           // weight ring slots per warp
+    int lcap;                         // capacity of a warp's stage list
+    int nb_max;                       // most blocks any CTA owns
     unsigned long long* dbg;          // optional globaltimer stamps (exl2b_debug_set), NULL in production
     int dbg_cta;
     unsigned short cta_blk[I8_MAX_CTAS + 1];      // CTA c owns 32-column blocks [cta_blk[c], cta_blk[c+1]) of the launch
 };
+
+// dynamic shared-memory map of a CTA (byte offsets, every region 16-byte aligned) -- one definition for host and device
+struct I8Smem {
+    uint32_t act, asum, ascale, emit, list, blksrc, total;
+};
+__host__ __device__ inline I8Smem i8_smem_map(int warps, int ns, int KS, int lcap, int nb_max) {
+    auto up = [](uint32_t x) { return (x + 15u) & ~15u; };
+    I8Smem m;
+    m.act = up((uint32_t)warps * (uint32_t)ns * I8_SLOT_BYTES);      // staged row: [KS][64 B]
+    m.asum = up(m.act + (uint32_t)KS * 64u);                          // [KS] integer sum of a slab's row values
+    m.ascale = up(m.asum + (uint32_t)KS * 4u);                        // [KS/4 + 1] scale of a 128-k block
+    m.emit = up(m.ascale + (uint32_t)(KS / 4 + 1) * 4u);              // [warp][2][32] partial sums of split blocks
+    m.list = up(m.emit + (uint32_t)warps * 256u);                     // [warp][lcap] stage descriptors
+    m.blksrc = up(m.list + (uint32_t)warps * (uint32_t)lcap * 8u);    // [nb_max] block streams
+    m.total = up(m.blksrc + (uint32_t)nb_max * 8u);
+    return m;
+}
 
 // ---- small device helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // a: 4 unsigned bytes, b: 4 signed bytes
@@ -237,7 +256,6 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     constexpr int I8_THREADS = I8_WARPS * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[I8_WARPS * I8_MAX_STAGES];
-    __shared__ int4 descs[I8_WARPS * I8_MAX_STAGES];       // stage descriptors: written at issue, read at consumption
     __shared__ float s_red[I8_WARPS];
     __shared__ int em_blk[I8_WARPS][2], em_n[I8_WARPS][2];
 
@@ -256,77 +274,103 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     const int units = nb * KS;
     const int l0 = (units * warp) / I8_WARPS, l1 = (units * (warp + 1)) / I8_WARPS;
 
-    const uint32_t ring = smem_addr(smem) + (uint32_t)warp * (uint32_t)(ns * I8_SLOT_BYTES);
-    const uint32_t bar0 = smem_addr(&bars[warp * I8_MAX_STAGES]);
-    const uint32_t desc0 = smem_addr(&descs[warp * I8_MAX_STAGES]);
-    int4* const my_descs = descs + warp * I8_MAX_STAGES;      // (written through the generic pointer by lane 0 at issue time)
-    uint8_t* const act_g = smem + (size_t)I8_WARPS * (size_t)(ns * I8_SLOT_BYTES);      // staged row: [KS][64 B]
-    int* const asum_s = reinterpret_cast<int*>(act_g + (size_t)KS * 64);                // [KS] integer sum of a slab's row values
-    float* const ascale_s = reinterpret_cast<float*>(asum_s + KS);                      // [KS/4 + 1] scale of a 128-k block
-    float* const emit_base = ascale_s + (KS / 4 + 1);                                   // [warp][2][32]
-    const uint32_t act = smem_addr(act_g), asum = smem_addr(asum_s), ascale = smem_addr(ascale_s);
+    // shared-memory map: generic pointers for the prologue's stores, 32-bit shared-space addresses (`lds*`) for the main loop
+    const I8Smem sm = i8_smem_map(I8_WARPS, ns, KS, P.lcap, P.nb_max);
+    uint8_t* const act_g = smem + sm.act;
+    int* const asum_s = reinterpret_cast<int*>(smem + sm.asum);
+    float* const ascale_s = reinterpret_cast<float*>(smem + sm.ascale);
+    float* const emit_base = reinterpret_cast<float*>(smem + sm.emit);
+    uint2* const list_g = reinterpret_cast<uint2*>(smem + sm.list) + (size_t)warp * P.lcap;
+    unsigned long long* const blksrc_g = reinterpret_cast<unsigned long long*>(smem + sm.blksrc);
+    uint32_t sbase;        // kept opaque: the compiler would otherwise re-derive every shared address from S2R in the loop
+    asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_addr(smem)));
+    const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)(ns * I8_SLOT_BYTES);
+    const uint32_t act = sbase + sm.act, asum = sbase + sm.asum, ascale = sbase + sm.ascale;
+    const uint32_t list = sbase + sm.list + (uint32_t)warp * (uint32_t)P.lcap * 8u;
+    uint32_t bar0;
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_addr(&bars[warp * I8_MAX_STAGES])));
 
-    // ---- issue cursor: (block i_b relative to blk0, slab i_ks), matrix i_mi and its current region cached in registers
-    int i_lin = l0, i_b = l0 / KS, i_ks = l0 - (l0 / KS) * KS, i_mi = 0, i_r = 0, islot = 0;
-    int r_begin, r_bits, r_spg, r_gbase, r_end;
-    uint32_t r_off;
-    const uint8_t* i_src;        // this block's byte stream
-    auto load_region = [&]() {
-        const I8Mat& m = P.mat[i_mi];
-        const QRegion& rg = m.reg[i_r];
-        r_begin = rg.ks_begin; r_bits = rg.bits; r_spg = rg.spg_log2; r_gbase = rg.group_base; r_off = rg.off_base;
-        r_end = (i_r + 1 < m.num_regions) ? m.reg[i_r + 1].ks_begin : KS;
-    };
-    auto load_block = [&]() {
-        const int blk = blk0 + i_b;
-        i_mi = 0;
+    // per-block table: byte stream of block b (and its matrix, in the low 2 bits: streams are 16-byte aligned)
+    for (int b = tid; b < nb; b += I8_THREADS) {
+        const int blk = blk0 + b;
+        int mi = 0;
 #pragma unroll
         for (int i = 1; i < I8_MAX_MATS; ++i)
-            if (i < P.num_mats && blk >= P.mat[i].blk_base) i_mi = i;
-        const I8Mat& m = P.mat[i_mi];
-        i_src = m.packed + (size_t)(blk - m.blk_base) * m.blk_stream_bytes;
-    };
-    load_block();
-    {
-        const I8Mat& m = P.mat[i_mi];
-#pragma unroll
-        for (int i = 1; i < MAX_REGIONS; ++i)
-            if (i < m.num_regions && i_ks >= m.reg[i].ks_begin) i_r = i;
+            if (i < P.num_mats && blk >= P.mat[i].blk_base) mi = i;
+        const I8Mat& m = P.mat[mi];
+        blksrc_g[b] = (unsigned long long)(m.packed + (size_t)(blk - m.blk_base) * m.blk_stream_bytes) | (unsigned long long)mi;
     }
-    load_region();
-    auto issue_one = [&]() {
-        const int rel = i_ks - r_begin, g = rel >> r_spg;
-        const int gend = r_begin + ((g + 1) << r_spg);
-        const int segend = min(min(gend, (i_ks | 3) + 1), min(r_end, i_ks + (l1 - i_lin)));
-        const int n = min(segend - i_ks, r_bits > 4 ? 2 : 4);          // <= I8_SLOT_BYTES
-        if (lane == 0) {
-            const uint32_t bar = bar0 + islot * 8;
-            const uint32_t bytes = (uint32_t)(n * 128 * r_bits);
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_copy_g2s(ring + (uint32_t)islot * I8_SLOT_BYTES, i_src + r_off + (uint32_t)(rel * 128 * r_bits), bytes, bar);
-            const int flags = ((i_ks + n == segend) ? DF_FLUSH : 0) | ((i_ks + n == KS || i_lin + n == l1) ? DF_BLOCK_DONE : 0);
-            my_descs[islot] = make_int4(n | (r_bits << 8) | (flags << 16), i_ks, r_gbase + g, (blk0 + i_b) | (i_mi << 24));
+
+    // ---- this warp's STAGE LIST, built here (nothing below depends on the previous launch): one 8-byte descriptor per stage
+    //        w0 = byte offset in the block stream | slabs << 22 | bits << 25 | flags << 29      w1 = ks | group << 11 | block << 22
+    //      so the main loop does no position arithmetic at all.  A stage is at most 2 KB (4 slabs up to 4 bits, 2 above) and
+    //      never crosses a quantisation group, a 128-k row block, a bit-width region or the end of the warp's range.
+    int nst = 0;
+    {
+        int lin = l0, b = l0 / KS, ks = l0 - (l0 / KS) * KS, mi = 0, r = 0;
+        auto set_block = [&]() {
+            const int blk = blk0 + b;
+            mi = 0;
+#pragma unroll
+            for (int i = 1; i < I8_MAX_MATS; ++i)
+                if (i < P.num_mats && blk >= P.mat[i].blk_base) mi = i;
+        };
+        int r_begin = 0, r_bits = 4, r_spg = 0, r_gbase = 0, r_end = 0;
+        uint32_t r_off = 0;
+        auto set_region = [&]() {
+            const I8Mat& m = P.mat[mi];
+            const QRegion& rg = m.reg[r];
+            r_begin = rg.ks_begin; r_bits = rg.bits; r_spg = rg.spg_log2; r_gbase = rg.group_base; r_off = rg.off_base;
+            r_end = (r + 1 < m.num_regions) ? m.reg[r + 1].ks_begin : KS;
+        };
+        if (lin < l1) {
+            set_block();
+            const I8Mat& m = P.mat[mi];
+#pragma unroll
+            for (int i = 1; i < MAX_REGIONS; ++i)
+                if (i < m.num_regions && ks >= m.reg[i].ks_begin) r = i;
+            set_region();
         }
-        i_lin += n;
-        i_ks += n;
-        islot = (islot + 1 == ns) ? 0 : islot + 1;
-        if (i_ks >= KS) {
-            i_ks = 0;
-            i_b++;
-            i_r = 0;
-            if (i_b < nb) { load_block(); load_region(); }
-        } else if (i_ks >= r_end) {
-            i_r++;
-            load_region();
+        while (lin < l1) {
+            const int rel = ks - r_begin, g = rel >> r_spg;
+            const int gend = r_begin + ((g + 1) << r_spg);
+            const int segend = min(min(gend, (ks | 3) + 1), min(r_end, ks + (l1 - lin)));
+            const int n = min(segend - ks, r_bits > 4 ? 2 : 4);
+            const uint32_t flags = ((ks + n == segend) ? DF_FLUSH : 0) | ((ks + n == KS || lin + n == l1) ? DF_BLOCK_DONE : 0);
+            if (nst >= P.lcap) __trap();
+            if (lane == 0)
+                list_g[nst] = make_uint2((r_off + (uint32_t)(rel * 128 * r_bits)) | ((uint32_t)n << 22) | ((uint32_t)r_bits << 25) | (flags << 29),
+                                         (uint32_t)ks | ((uint32_t)(r_gbase + g) << 11) | ((uint32_t)b << 22));
+            ++nst;
+            lin += n;
+            ks += n;
+            if (ks >= KS) {
+                ks = 0;
+                ++b;
+                r = 0;
+                if (lin < l1) { set_block(); set_region(); }
+            } else if (ks >= r_end) {
+                ++r;
+                set_region();
+            }
         }
+    }
+    __syncthreads();          // block table + stage lists visible
+    auto issue_stage = [&](int s, int slot_idx) {          // lane 0: request stage s into ring slot slot_idx
+        const uint2 d = lds64(list + (uint32_t)s * 8u);
+        const uint32_t bytes = ((d.x >> 22) & 7u) * 128u * ((d.x >> 25) & 15u);
+        const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (d.y >> 22));
+        const uint32_t bar = bar0 + (uint32_t)slot_idx * 8u;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_copy_g2s(ring + (uint32_t)slot_idx * I8_SLOT_BYTES, reinterpret_cast<const uint8_t*>(src & ~3ull) + (d.x & 0x3fffffu), bytes, bar);
     };
-    // weight requests for the first stages (nothing here depends on the previous launch)
-    for (int i = 0; i < ns && i_lin < l1; ++i) issue_one();
-    __syncwarp();
+    if (lane == 0)
+        for (int i = 0; i < ns && i < nst; ++i) issue_stage(i, i);
     RawScale raw = {0u, __ushort_as_half(0)};
-    if (l0 < l1) {
-        const uint4 d0 = lds128(desc0);
-        raw = load_scales(P, (int)(d0.w >> 24), (int)(d0.w & 0xffffffu), (int)d0.z, lane);
+    if (nst > 0) {
+        const uint2 d0 = lds64(list);
+        const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (d0.y >> 22));
+        raw = load_scales(P, (int)(src & 3ull), blk0 + (int)(d0.y >> 22), (int)((d0.y >> 11) & 0x7ffu), lane);
     }
 
     // ---- static operands of the prologue, fetched before the dependency wait: permutation indices (when the row has to be
@@ -492,16 +536,16 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         rrms = rsqrtf(t * (1.0f / (float)P.K) + P.norm_eps);
     }
 
-    // ---- main loop: this warp alone, stage by stage.  Everything positional comes from the descriptor written at issue time.
+    // ---- main loop: this warp alone, stage by stage; everything positional comes from the stage list.
     int am[4] = {0, 0, 0, 0}, ae[2] = {0, 0};
     float tot = 0.f;
-    int S = 0, cslot = 0, blk_slabs = 0, emits = 0, c_lin = l0;
+    int S = 0, cslot = 0, blk_slabs = 0, emits = 0;
     uint32_t phase = 0;
-    while (c_lin < l1) {
-        mbar_wait(bar0 + cslot * 8, (phase >> cslot) & 1u);
+    for (int s = 0; s < nst; ++s) {
+        mbar_wait(bar0 + (uint32_t)cslot * 8u, (phase >> cslot) & 1u);
         phase ^= 1u << cslot;
-        const uint4 d = lds128(desc0 + cslot * 16);
-        const int n = d.x & 0xff, bits = (d.x >> 8) & 0xff, flags = d.x >> 16, ks = (int)d.y;
+        const uint2 d = lds64(list + (uint32_t)s * 8u);
+        const int n = (int)((d.x >> 22) & 7u), bits = (int)((d.x >> 25) & 15u), ks = (int)(d.y & 0x7ffu);
         const uint32_t slot = ring + (uint32_t)cslot * I8_SLOT_BYTES;
         const uint32_t xs = act + (uint32_t)ks * 64u, as = asum + (uint32_t)ks * 4u;
         switch (bits) {
@@ -513,16 +557,15 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
             default: S += consume_stage<2>(slot, n, xs, as, lane, am, ae); break;
         }
         __syncwarp();
-        if (i_lin < l1) issue_one();            // refill the slot just drained (islot == cslot here)
-        __syncwarp();
-        c_lin += n;
-        blk_slabs += n;
+        if (lane == 0 && s + ns < nst) issue_stage(s + ns, cslot);            // refill the slot just drained
         cslot = (cslot + 1 == ns) ? 0 : cslot + 1;
-        if (flags & DF_FLUSH) {
+        blk_slabs += n;
+        if (d.x & ((uint32_t)DF_FLUSH << 29)) {
             // integer sums -> fp32:  sum_k a_k (q_k - zero) * scale  =  (sum a q - zero * sum a) * scale_w * scale_row
-            const int mi = (int)(d.w >> 24), blk = (int)(d.w & 0xffffffu);
-            const I8Mat& m = P.mat[mi];
-            const int col = (blk - m.blk_base) * 32 + lane;
+            const int b = (int)(d.y >> 22);
+            const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + b);
+            const I8Mat& m = P.mat[(int)(src & 3ull)];
+            const int col = (blk0 + b - m.blk_base) * 32 + lane;
             int v = ((am[0] << 8) + am[1]) + (((am[2] << 8) + am[3]) >> 4) + (((ae[0] << 8) + ae[1]) << plane_main(bits));
             const uint32_t nib = (raw.w >> ((col & 7) * 4)) & 15u;
             float ws;
@@ -540,17 +583,18 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
             am[0] = am[1] = am[2] = am[3] = 0;
             ae[0] = ae[1] = 0;
             S = 0;
-            if (c_lin < l1) {                  // scales of the next segment (its descriptor is already in the ring)
-                const uint4 dn = lds128(desc0 + cslot * 16);
-                raw = load_scales(P, (int)(dn.w >> 24), (int)(dn.w & 0xffffffu), (int)dn.z, lane);
+            if (s + 1 < nst) {                 // scales of the next segment
+                const uint2 dn = lds64(list + (uint32_t)(s + 1) * 8u);
+                const unsigned long long sn = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (dn.y >> 22));
+                raw = load_scales(P, (int)(sn & 3ull), blk0 + (int)(dn.y >> 22), (int)((dn.y >> 11) & 0x7ffu), lane);
             }
-            if (flags & DF_BLOCK_DONE) {
+            if (d.x & ((uint32_t)DF_BLOCK_DONE << 29)) {
                 if (blk_slabs == KS) {
-                    finalize_block(P, blk, lane, tot * rrms);          // this warp covered the block's whole K by itself
+                    finalize_block(P, blk0 + b, lane, tot * rrms);          // this warp covered the block's whole K by itself
                 } else {
                     if (emits >= 2) __trap();       // a warp's range has at most two partial blocks (its first and its last)
                     emit_base[(warp * 2 + emits) * 32 + lane] = tot;
-                    if (lane == 0) { em_blk[warp][emits] = blk; em_n[warp][emits] = blk_slabs; }
+                    if (lane == 0) { em_blk[warp][emits] = blk0 + b; em_n[warp][emits] = blk_slabs; }
                     ++emits;
                 }
                 tot = 0.f;
@@ -708,10 +752,22 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     int C = 0;
     i8_partition_blocks(blk_bytes, sms, P.cta_blk, &C);
 
-    // shared memory: weight rings + staged row (64 B + sum per slab, scale per 128 k) + per-warp partials
-    const size_t act_bytes = (size_t)P.KS * 64 + (size_t)P.KS * 4 + (size_t)(P.KS / 4 + 1) * 4;
-    const size_t emit_bytes = (size_t)warps * 2 * 32 * sizeof(float);
-    auto smem_for = [&](int ns) { return (size_t)warps * ns * I8_SLOT_BYTES + act_bytes + emit_bytes; };
+    // shared memory: i8_smem_map (weight rings, staged row, per-warp partials, stage lists, block table)
+    // stage-list capacity: an upper bound of the stages one warp can have (every boundary a stage may not cross adds at most one)
+    int nb_max = 0, smin = 4, max_regions = 1;
+    for (int c = 0; c < C; ++c) nb_max = std::max(nb_max, (int)P.cta_blk[c + 1] - (int)P.cta_blk[c]);
+    for (int i = 0; i < nm; ++i) {
+        max_regions = std::max(max_regions, P.mat[i].num_regions);
+        for (int r = 0; r < P.mat[i].num_regions; ++r) {
+            smin = std::min(smin, std::min(1 << P.mat[i].reg[r].spg_log2, P.mat[i].reg[r].bits > 4 ? 2 : 4));
+            if (P.mat[i].reg[r].ks_begin & 3) smin = 1;      // groups not aligned with the 128-k row blocks: segments may be single slabs
+        }
+    }
+    const int upw = (nb_max * P.KS + warps - 1) / warps + 1;
+    P.lcap = (upw + smin - 1) / smin + (upw / P.KS + 2) * (max_regions + 1) + 4;
+    P.nb_max = nb_max;
+    EXL2B_REQUIRE(P.KS <= 2048 && nb_max < 1024, "matrix too large for the stage descriptor (K <= 65536)");
+    auto smem_for = [&](int ns) { return (size_t)i8_smem_map(warps, ns, P.KS, P.lcap, P.nb_max).total; };
     // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: the deepest ring
     // (<= 4 slots per warp) that keeps the CTA <= 112 KB, never fewer than 2 slots
     P.ns = I8_MAX_STAGES;

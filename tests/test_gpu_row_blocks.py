@@ -317,7 +317,10 @@ def test_gptq_4096_row(act_order):
     torch.cuda.synchronize()
     e_ref = oracle.rel_l2(c_ref.cpu().numpy(), truth)
     e_new = oracle.rel_l2(got.cpu().numpy(), c_ref.float().cpu().numpy())
-    assert e_new <= TOL, f"vs reference kernel: {e_new:.2e}"
+    # the reference kernel accumulates in fp16 with atomics: it sits ~1e-3 from the truth itself.  The contract:
+    # closer to the truth than the reference, and no further from the reference than the two distances to the truth allow
     assert err <= e_ref + 1e-4, f"further from the truth ({err:.2e}) than the reference kernel ({e_ref:.2e})"
+    assert e_new <= e_ref + err + 1e-4, f"vs reference kernel: {e_new:.2e} (reference vs truth {e_ref:.2e}, ours vs truth {err:.2e})"
+    assert e_new <= 2e-3
     ref.free_q_matrix(hr)
     lin.unload()
