@@ -21,6 +21,9 @@
 
 namespace exl2b {
 
+extern unsigned long long* g_dbg;
+extern int g_dbg_cta, g_dbg_slot;
+
 constexpr int AQ_THREADS = 256;
 constexpr int AQ_WARPS = 8;
 constexpr int AQ_MAX_QLEN = 8;
@@ -53,7 +56,16 @@ struct AttnQ4Params {
     int nsplit;
     float* ws;              // [batch][H][nsplit][hd + 2]
     unsigned int* cnt;      // [batch][H]
+    unsigned long long* dbg;   // optional globaltimer stamps of CTA (dbg_cta, 0, 0) (exl2b_debug_set): 0 start, 1 cache rows requested,
+    int dbg_cta;               //   2 dependency wait over, 3 new rows quantised / query rotated, 4 scores + max, 5 P V done; 6 / 7 grid span
 };
+__device__ __forceinline__ unsigned long long aq_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define AQ_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) P.dbg[i] = aq_gtimer(); \
+                                      if ((i) == 0 && threadIdx.x == 0) atomicMin(P.dbg + 6, aq_gtimer()); } } while (0)
 constexpr int AQ_SPLIT_MIN = 512;
 
 // one half2 (elements un*64 + 2*lane, +1) of a head row, rotated if RoPE is fused.  Warp-uniform call.
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     int* pages_s = reinterpret_cast<int*>(new_y + 2 * AQ_MAX_QLEN * HD);   // [pages_per_seq]
     float* sc = reinterpret_cast<float*>(pages_s + ((P.pages_per_seq + 3) & ~3));   // [max_ctx + q_len]
 
+    AQ_STAMP(0);
     griddep_launch_dependents();
     // ---- 0. before the dependency wait: everything that only touches state written by EARLIER steps / layers -- the
     //      sequence length, the page table and the cached rows (this layer's cache was last written one decode step ago; the
@@ -188,7 +201,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     }
     for (int i = tid; i < P.pages_per_seq; i += AQ_THREADS) pages_s[i] = btg[i];
     const int* bt = pages_s;
+    AQ_STAMP(1);
     griddep_wait();
+    AQ_STAMP(2);
 
     // ---- 1. quantise the new rows (fp16_to_q_kv arithmetic) on the first warps, keep them in shared memory; at the same
     //      time the LAST warps rotate the first query: qrot = H q * (softmax_scale * log2 e / 32)
@@ -227,6 +242,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         if ((lane & 15) == 0) new_s[(kv * AQ_MAX_QLEN + i) * NSC + un * 2 + (lane >> 4)] = __hmul(absmax, __float2half_rn(1.0f / 8.0f));
     }
     __syncthreads();
+    AQ_STAMP(3);
     if (h % group == 0 && z == 0) {
         for (int idx = tid; idx < 2 * P.q_len * (ROWB / 4); idx += AQ_THREADS) {
             const int kv = idx / (P.q_len * (ROWB / 4)), r = idx - kv * P.q_len * (ROWB / 4);
@@ -315,6 +331,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         if (lane == 0) wred[warp] = lmax;
         __syncthreads();
+        AQ_STAMP(4);
         float mx = wred[0];
 #pragma unroll
         for (int w = 1; w < AQ_WARPS; ++w) mx = fmaxf(mx, wred[w]);
@@ -385,6 +402,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < VEC; ++j) red[warp * HD + lane * VEC + j] = acc[j];
         __syncthreads();
+        AQ_STAMP(5);
         // ---- 5. sum over warps, (merge the splits,) rotate back (x = H y / 32), normalise, store ----
         if (ns_act > 1) {
             // leave (unnormalised rotated output, max, sum) of this chunk; the last CTA of the (head, sequence) merges them all
@@ -466,6 +484,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         }
         __syncthreads();
     }
+    if (P.dbg && threadIdx.x == 0) atomicMax(P.dbg + 7, aq_gtimer());
 }
 
 }  // namespace exl2b
@@ -574,6 +593,10 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
         P.cnt = g_cnt[dev];
     }
     P.nsplit = nsplit;
+    {
+        P.dbg = exl2b::g_dbg ? exl2b::g_dbg + 32 * (exl2b::g_dbg_slot++ % 64) : nullptr;
+        P.dbg_cta = 0;
+    }
     const int sc_len = nsplit > 1 ? std::max(AQ_SPLIT_MIN, (P.max_ctx + nsplit) / nsplit) + 8 : P.max_ctx + q_len;
     const int hd = head_dim;
     const size_t smem = (size_t)(hd + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +

@@ -104,6 +104,25 @@ __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
 template <int BITS>
 __device__ __forceinline__ void consume_slab(uint32_t wb, uint32_t xs, int lane, int (&am)[4], int (&ae)[2]) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
+    if constexpr (BITS == 4) {
+        // the common case, in two halves of the slab so that only 8 row words are live at a time (64 registers per thread)
+        const uint4 w4 = lds128(wb + lane * 16);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const uint4 xh = lds128(xs + hf * 16), xl = lds128(xs + 32 + hf * 16);
+            const uint32_t wa = hf ? w4.z : w4.x, wc = hf ? w4.w : w4.y;
+            const uint32_t lo0 = wa & 0x0f0f0f0fu, hi0 = wa & 0xf0f0f0f0u, lo1 = wc & 0x0f0f0f0fu, hi1 = wc & 0xf0f0f0f0u;
+            am[0] = dp4a_us(lo0, xh.x, am[0]);
+            am[1] = dp4a_uu(lo0, xl.x, am[1]);
+            am[2] = dp4a_us(hi0, xh.y, am[2]);
+            am[3] = dp4a_uu(hi0, xl.y, am[3]);
+            am[0] = dp4a_us(lo1, xh.z, am[0]);
+            am[1] = dp4a_uu(lo1, xl.z, am[1]);
+            am[2] = dp4a_us(hi1, xh.w, am[2]);
+            am[3] = dp4a_uu(hi1, xl.w, am[3]);
+        }
+        return;
+    }
     uint32_t XH[8], XL[8];
     {
         const uint4 h0 = lds128(xs), h1 = lds128(xs + 16), l0 = lds128(xs + 32), l1 = lds128(xs + 48);

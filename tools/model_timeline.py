@@ -26,15 +26,15 @@ torch.cuda.synchronize()
 stamps.zero_(); stamps[:, 6] = 2**62
 dec.decode(ids); torch.cuda.synchronize()
 st = stamps.cpu().tolist()
-n = 4 * layers + 1
-names = ["qkv", "o", "gateup", "down"]
+n = 5 * layers + 1
+names = ["qkv", "attn", "o", "gateup", "down"]
 t0 = st[0][6]
 # the warm-up step in capture() used the first n slots; the captured graph the next n
 rows = [r for r in st if r[6] < 2**62]
 print("launches with stamps:", len(rows))
 prev_end = None
 for i, r in enumerate(rows):
-    nm = names[i % 4] if i < 4 * layers else "head"
+    nm = names[i % 5] if i < 5 * layers else "head"
     gs, ge = r[6] - rows[0][6], r[7] - rows[0][6]
     c = [x - rows[0][6] if x else None for x in r[0:6]]
     print(f"{i:3d} {nm:7s} grid {gs/1e3:8.2f} -> {ge/1e3:8.2f} us  dur {(ge-gs)/1e3:6.2f}  gap_from_prev_end {((gs-prev_end)/1e3 if prev_end is not None else 0):6.2f}  cta0 "
