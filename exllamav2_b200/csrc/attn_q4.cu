@@ -53,6 +53,7 @@ struct AttnQ4Params {
     // split-KV (long contexts, q_len == 1): grid.z CTAs share one (head, sequence); each attends a contiguous chunk of positions
     // and leaves (max, sum, unnormalised rotated output) in `ws`; the last to arrive (counter) merges.  Chunks are at least
     // AQ_SPLIT_MIN positions, so short contexts use one CTA and never touch the workspace.
+    int sc_len;             // floats of the score buffer
     int nsplit;
     float* ws;              // [batch][H][nsplit][hd + 2]
     unsigned int* cnt;      // [batch][H]
@@ -67,6 +68,15 @@ __device__ __forceinline__ unsigned long long aq_gtimer() {
 #define AQ_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) P.dbg[i] = aq_gtimer(); \
                                       if ((i) == 0 && threadIdx.x == 0) atomicMin(P.dbg + 6, aq_gtimer()); } } while (0)
 constexpr int AQ_SPLIT_MIN = 512;
+constexpr int AQ_STAGE = 512;          // cached positions per CTA staged in shared memory before the dependency wait
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
 
 // one half2 (elements un*64 + 2*lane, +1) of a head row, rotated if RoPE is fused.  Warp-uniform call.
 template <int HD>
@@ -140,14 +150,19 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     const int group = P.H / P.KVH, kvh = h / group;
     __shared__ int s_last;
 
-    float* qrot = reinterpret_cast<float*>(smem);                          // [HD]
-    float* red = qrot + HD;                                                // [AQ_WARPS][HD]
+    constexpr int QPAD = 36;               // floats per 32-value block of the rotated query (bank-staggered: 4 blocks, 4 threads per row)
+    float* qrot = reinterpret_cast<float*>(smem);                          // [NSC][QPAD]
+    float* red = qrot + NSC * QPAD;                                                // [AQ_WARPS][HD]
     float* wred = red + AQ_WARPS * HD;                                     // [2 * AQ_WARPS]
     uint8_t* new_q = reinterpret_cast<uint8_t*>(wred + 2 * AQ_WARPS);      // [2][AQ_MAX_QLEN][ROWB]
     half* new_s = reinterpret_cast<half*>(new_q + 2 * AQ_MAX_QLEN * ROWB); // [2][AQ_MAX_QLEN][NSC]
     float* new_y = reinterpret_cast<float*>(new_s + 2 * AQ_MAX_QLEN * NSC);// [2][AQ_MAX_QLEN][HD] rotated, unquantised new rows
     int* pages_s = reinterpret_cast<int*>(new_y + 2 * AQ_MAX_QLEN * HD);   // [pages_per_seq]
-    float* sc = reinterpret_cast<float*>(pages_s + ((P.pages_per_seq + 3) & ~3));   // [max_ctx + q_len]
+    float* sc = reinterpret_cast<float*>(pages_s + ((P.pages_per_seq + 3) & ~3));   // [sc_len]
+    uint8_t* kst = reinterpret_cast<uint8_t*>(sc + ((P.sc_len + 3) & ~3));            // [AQ_STAGE][ROWB]  staged cached K rows
+    uint8_t* vst = kst + AQ_STAGE * ROWB;                                            // [AQ_STAGE][ROWB]
+    half* ksst = reinterpret_cast<half*>(vst + AQ_STAGE * ROWB);                     // [AQ_STAGE][NSC]
+    half* vsst = ksst + AQ_STAGE * NSC;
 
     AQ_STAMP(0);
     griddep_launch_dependents();
@@ -172,32 +187,28 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         p_hi = min(n_all, p_lo + chunk);
     }
     const int c_hi = min(p_hi, seqlen);          // cached rows of this CTA: [p_lo, c_hi)
-    constexpr int PV_UNROLL = 8;
-    uint4 kpre[NSC];                   // the cached K row this thread currently holds (position k_held)
-    uint2 kspre = make_uint2(0u, 0u);
-    int k_held = -1;
-    if (p_lo + tid < c_hi) {
-        k_held = p_lo + tid;
-        const int page = btg[k_held / P.page_size];
-        const size_t row = ((size_t)page * P.page_size + k_held % P.page_size) * P.KVH + kvh;
-#pragma unroll
-        for (int blk = 0; blk < NSC; ++blk) kpre[blk] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + blk);
-        if constexpr (NSC == 4) kspre = __ldg(reinterpret_cast<const uint2*>(P.k_s + row * NSC));
-        else kspre.x = __ldg(reinterpret_cast<const uint32_t*>(P.k_s + row * NSC));
-    }
-    uint32_t vpre[PV_UNROLL];          // packed nibbles of my VEC values | fp16 scale << 16
-#pragma unroll
-    for (int u = 0; u < PV_UNROLL; ++u) {
-        const int p = p_lo + warp + u * AQ_WARPS;
-        vpre[u] = 0x8888u;
-        if (p < c_hi) {
-            const int page = btg[p / P.page_size];
-            const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
-            uint32_t x;
-            if constexpr (VEC == 4) x = __ldg(reinterpret_cast<const uint16_t*>(P.v_q + row * ROWB + lane * 2));
-            else x = (uint32_t)__ldg(P.v_q + row * ROWB + lane) | 0x8800u;
-            vpre[u] = x | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(P.v_s + row * NSC + ((lane * VEC) >> 5))) << 16);
+    // The first AQ_STAGE cached positions of this CTA are copied to shared memory with cp.async (no registers held across the
+    // wait): K / V nibbles [pos][ROWB] and their fp16 scales [pos][NSC].
+    constexpr int TPR = NSC, RPP = AQ_THREADS / TPR;      // scores: NSC threads per position (one 32-value block + scale each)
+    const int kblk = tid & (TPR - 1), krow = tid / TPR;
+    const int n_st = max(0, min(c_hi - p_lo, AQ_STAGE));
+    {
+        constexpr int CH = ROWB / 16;
+        for (int idx = tid; idx < n_st * CH; idx += AQ_THREADS) {
+            const int pos = idx / CH, ch = idx - pos * CH, pp = p_lo + pos;
+            const int page = btg[pp / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + pp % P.page_size) * P.KVH + kvh;
+            cp_async16(smem_addr(kst + pos * ROWB + ch * 16), P.k_q + row * ROWB + ch * 16);
+            cp_async16(smem_addr(vst + pos * ROWB + ch * 16), P.v_q + row * ROWB + ch * 16);
         }
+        for (int pos = tid; pos < n_st; pos += AQ_THREADS) {
+            const int pp = p_lo + pos;
+            const int page = btg[pp / P.page_size];
+            const size_t row = ((size_t)page * P.page_size + pp % P.page_size) * P.KVH + kvh;
+            cp_async_small<NSC * 2>(smem_addr(ksst + pos * NSC), P.k_s + row * NSC);
+            cp_async_small<NSC * 2>(smem_addr(vsst + pos * NSC), P.v_s + row * NSC);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int i = tid; i < P.pages_per_seq; i += AQ_THREADS) pages_s[i] = btg[i];
     const int* bt = pages_s;
@@ -211,8 +222,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         const half2 qh = load_roped<HD>(P.q + (((size_t)b * P.q_len + i) * P.H + h) * HD, un, lane, P, seqlen + i);
         float2 w = hadamard32_f(__half22float2(qh), lane);
         const float f = P.scale_log2 * (1.0f / 32.0f);
-        qrot[un * 64 + 2 * lane] = w.x * f;
-        qrot[un * 64 + 2 * lane + 1] = w.y * f;
+        const int e = un * 64 + 2 * lane;
+        qrot[(e >> 5) * QPAD + (e & 31)] = w.x * f;
+        qrot[(e >> 5) * QPAD + (e & 31) + 1] = w.y * f;
     };
     if (warp >= AQ_WARPS - UNITS) rotate_q(0, warp - (AQ_WARPS - UNITS));
     const int n_jobs = 2 * P.q_len * UNITS;
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         new_q[(kv * AQ_MAX_QLEN + i) * ROWB + un * 32 + lane] = (uint8_t)(q0 | (q1 << 4));
         if ((lane & 15) == 0) new_s[(kv * AQ_MAX_QLEN + i) * NSC + un * 2 + (lane >> 4)] = __hmul(absmax, __float2half_rn(1.0f / 8.0f));
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     AQ_STAMP(3);
     if (h % group == 0 && z == 0) {
@@ -263,31 +276,26 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         }
     }
 
-    // score of one cached row held in registers (4-bit values against the rotated query)
-    auto score_row = [&](const uint4* kq4, uint2 ks2) {
-        float s = 0.f;
-        const half* ksh = reinterpret_cast<const half*>(&ks2);
+    // score of one 32-value block of a cached row (4-bit values, one fp16 scale) against its block of the rotated query
+    auto score_blk = [&](uint4 kq, uint32_t ks) {
+        const float* qb_ = qrot + kblk * QPAD;
+        const uint32_t ww[4] = {kq.x, kq.y, kq.z, kq.w};
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int blk = 0; blk < NSC; ++blk) {
-            const uint32_t ww[4] = {kq4[blk].x, kq4[blk].y, kq4[blk].z, kq4[blk].w};
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 qa = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8);
-                const float4 qb = *reinterpret_cast<const float4*>(qrot + blk * 32 + j * 8 + 4);
-                const uint32_t x = ww[j];
-                a0 = fmaf(nib_f(x & 15u), qa.x, a0);
-                a1 = fmaf(nib_f((x >> 4) & 15u), qa.y, a1);
-                a0 = fmaf(nib_f((x >> 8) & 15u), qa.z, a0);
-                a1 = fmaf(nib_f((x >> 12) & 15u), qa.w, a1);
-                a0 = fmaf(nib_f((x >> 16) & 15u), qb.x, a0);
-                a1 = fmaf(nib_f((x >> 20) & 15u), qb.y, a1);
-                a0 = fmaf(nib_f((x >> 24) & 15u), qb.z, a0);
-                a1 = fmaf(nib_f(x >> 28), qb.w, a1);
-            }
-            s = fmaf(__half2float(ksh[blk]), a0 + a1, s);
+        for (int j = 0; j < 4; ++j) {
+            const float4 qa = *reinterpret_cast<const float4*>(qb_ + j * 8);
+            const float4 qb = *reinterpret_cast<const float4*>(qb_ + j * 8 + 4);
+            const uint32_t x = ww[j];
+            a0 = fmaf(nib_f(x & 15u), qa.x, a0);
+            a1 = fmaf(nib_f((x >> 4) & 15u), qa.y, a1);
+            a2 = fmaf(nib_f((x >> 8) & 15u), qa.z, a2);
+            a3 = fmaf(nib_f((x >> 12) & 15u), qa.w, a3);
+            a0 = fmaf(nib_f((x >> 16) & 15u), qb.x, a0);
+            a1 = fmaf(nib_f((x >> 20) & 15u), qb.y, a1);
+            a2 = fmaf(nib_f((x >> 24) & 15u), qb.z, a2);
+            a3 = fmaf(nib_f(x >> 28), qb.w, a3);
         }
-        return s;
+        return __half2float(__ushort_as_half((unsigned short)ks)) * ((a0 + a1) + (a2 + a3));
     };
 
     for (int i = 0; i < P.q_len; ++i) {
@@ -297,35 +305,71 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
             __syncthreads();
         }
 
-        // ---- 2. scores: one position per thread, the whole (rotated) row against qrot ----
+        // ---- 2. scores: NSC threads per position, each its 32-value block of the (rotated) row against qrot ----
         float lmax = -INFINITY;
-        for (int p = p_lo + tid; p < n_ctx; p += AQ_THREADS) {
-            float s;
-            if (p >= seqlen) {                   // a row appended by this step: fp16 values, rotated in fp32
-                const float* y = new_y + (p - seqlen) * HD;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-                for (int j = 0; j < HD; j += 4) {
-                    s0 = fmaf(qrot[j], y[j], s0);
-                    s1 = fmaf(qrot[j + 1], y[j + 1], s1);
-                    s2 = fmaf(qrot[j + 2], y[j + 2], s2);
-                    s3 = fmaf(qrot[j + 3], y[j + 3], s3);
-                }
-                s = (s0 + s1) + (s2 + s3);
-            } else {
-                if (p != k_held) {               // (the first row of every thread was fetched before the dependency wait)
-                    const int page = bt[p / P.page_size];
-                    const size_t row = ((size_t)page * P.page_size + p % P.page_size) * P.KVH + kvh;
+        auto score_pos = [&](int p, uint4 kq, uint32_t ks) {      // warp-uniform call (the NSC partial sums meet by shuffle)
+            float s = 0.f;
+            if (p < n_ctx) {
+                if (p >= seqlen) {               // a row appended by this step: fp16 values, rotated in fp32
+                    const float* y = new_y + (p - seqlen) * HD + kblk * 32;
+                    const float* qb_ = qrot + kblk * QPAD;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int blk = 0; blk < NSC; ++blk) kpre[blk] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + blk);
-                    if constexpr (NSC == 4) kspre = __ldg(reinterpret_cast<const uint2*>(P.k_s + row * NSC));
-                    else kspre.x = __ldg(reinterpret_cast<const uint32_t*>(P.k_s + row * NSC));
-                    k_held = p;
+                    for (int j = 0; j < 32; j += 4) {
+                        s0 = fmaf(qb_[j], y[j], s0);
+                        s1 = fmaf(qb_[j + 1], y[j + 1], s1);
+                        s2 = fmaf(qb_[j + 2], y[j + 2], s2);
+                        s3 = fmaf(qb_[j + 3], y[j + 3], s3);
+                    }
+                    s = (s0 + s1) + (s2 + s3);
+                } else {
+                    s = score_blk(kq, ks);
                 }
-                s = score_row(kpre, kspre);
             }
-            sc[p - p_lo] = s;
-            lmax = fmaxf(lmax, s);
+#pragma unroll
+            for (int o = 1; o < TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (p < n_ctx) {
+                if (kblk == 0) sc[p - p_lo] = s;
+                lmax = fmaxf(lmax, s);
+            }
+        };
+        {
+            const int st_end = p_lo + n_st;                      // positions below are in shared memory
+            int pb = p_lo;
+            for (; pb < n_ctx && pb < st_end; pb += RPP) {
+                const int pp = pb + krow;
+                uint4 kq = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+                uint32_t ks = 0u;
+                if (pp < st_end) {
+                    kq = *reinterpret_cast<const uint4*>(kst + (pp - p_lo) * ROWB + kblk * 16);
+                    ks = *reinterpret_cast<const unsigned short*>(ksst + (pp - p_lo) * NSC + kblk);
+                } else if (pp < min(n_ctx, seqlen)) {
+                    const int page = bt[pp / P.page_size];
+                    const size_t row = ((size_t)page * P.page_size + pp % P.page_size) * P.KVH + kvh;
+                    kq = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + kblk);
+                    ks = __ldg(reinterpret_cast<const unsigned short*>(P.k_s + row * NSC) + kblk);
+                }
+                score_pos(pp, kq, ks);
+            }
+            for (; pb < n_ctx; pb += 2 * RPP) {                  // beyond the staged window: two passes in flight
+                uint4 kq[2];
+                uint32_t ks[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int pp = pb + u * RPP + krow;
+                    kq[u] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+                    ks[u] = 0u;
+                    if (pp < min(n_ctx, seqlen)) {
+                        const int page = bt[pp / P.page_size];
+                        const size_t row = ((size_t)page * P.page_size + pp % P.page_size) * P.KVH + kvh;
+                        kq[u] = __ldg(reinterpret_cast<const uint4*>(P.k_q + row * ROWB) + kblk);
+                        ks[u] = __ldg(reinterpret_cast<const unsigned short*>(P.k_s + row * NSC) + kblk);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (pb + u * RPP < n_ctx) score_pos(pb + u * RPP + krow, kq[u], ks[u]);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -365,12 +409,19 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
                 acc[1] = fmaf(pe, nib_f((xs >> 4) & 15u), acc[1]);
             }
         };
-#pragma unroll
-        for (int u = 0; u < PV_UNROLL; ++u) {                                 // rows prefetched before the dependency wait
-            const int p = p_lo + warp + u * AQ_WARPS;
-            if (p < c_hi) pv_fma(vpre[u], sc[p - p_lo]);
+        {
+            const int st_end = p_lo + n_st;                      // staged rows: shared memory
+#pragma unroll 4
+            for (int p = p_lo + warp; p < st_end; p += AQ_WARPS) {
+                const int r = p - p_lo;
+                uint32_t x;
+                if constexpr (VEC == 4) x = *reinterpret_cast<const uint16_t*>(vst + r * ROWB + lane * 2);
+                else x = (uint32_t)vst[r * ROWB + lane] | 0x8800u;
+                x |= (uint32_t)(*reinterpret_cast<const uint16_t*>(vsst + r * NSC + ((lane * VEC) >> 5))) << 16;
+                pv_fma(x, sc[r]);
+            }
         }
-        for (int p0 = p_lo + warp + PV_UNROLL * AQ_WARPS; p0 < c_hi; p0 += AQ_WARPS * 8) {   // longer contexts: 8 rows in flight
+        for (int p0 = p_lo + n_st + warp; p0 < c_hi; p0 += AQ_WARPS * 8) {   // longer contexts: 8 rows in flight
             uint32_t xs[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -599,8 +650,10 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
     }
     const int sc_len = nsplit > 1 ? std::max(AQ_SPLIT_MIN, (P.max_ctx + nsplit) / nsplit) + 8 : P.max_ctx + q_len;
     const int hd = head_dim;
-    const size_t smem = (size_t)(hd + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
-                        (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)sc_len * 4;
+    P.sc_len = sc_len;
+    const size_t smem = (size_t)((hd / 32) * 36 + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
+                        (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)((sc_len + 3) & ~3) * 4 +
+                        (size_t)AQ_STAGE * (hd / 2) * 2 + (size_t)AQ_STAGE * (hd / 32) * 2 * 2;
     EXL2B_REQUIRE(smem <= 200 * 1024, "context of %d tokens does not fit the score buffer", P.max_ctx);
     static bool attr_set[64] = {false};
     if (!attr_set[dev]) {

@@ -24,7 +24,12 @@
 //     private 3-stage ring and never synchronises with another warp in the main loop.
 //   * when the producer of the row scattered a copy in this matrix's stored-row order (I8Out::c_perm), the prologue reads the
 //     row with one 16-byte load per thread instead of eight 2-byte gathers.
+#include <string.h>
+
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "gemv_i8.cuh"
@@ -34,25 +39,30 @@ namespace exl2b {
 constexpr int I8_MAX_WARPS = 16;
 constexpr int I8_MAX_STAGES = 4;
 constexpr int I8_MAX_CTAS = 160;
-constexpr int I8_SLOT_BYTES = 2048;       // one stage: 4 slabs (128 k) at <= 4 bits, 2 slabs above
 
 struct I8Mat {
     const uint8_t* packed;
-    const uint32_t* q_scale;
-    const half* q_scale_max;
-    const uint32_t* qzeros;
-    const half* gptq_scales;
+    const void* wtab;                 // dense scale table (QMatrix::wtab): EXL2 fp16[G][N], GPTQ uint32[G][N]
     const half* bias;
     half* c;
     half* c_perm;
     const uint16_t* out_invperm;
-    uint32_t blk_stream_bytes;
-    int N, blk_base, is_gptq, clear, num_regions;
-    QRegion reg[MAX_REGIONS];
+    int N, blk_base, clear;
 };
+
+// One stage of a warp's work = one bulk copy = up to 4 slabs of one 32-column block with one bit width, inside one
+// quantisation group and one 128-k row block.  16 bytes, built ON THE HOST once per launch structure (I8Plan below):
+//   x = byte offset of the stage inside its matrix' packed buffer
+//   y = element index of lane 0's entry in the matrix' scale table (group * N + first column of the block)
+//   z = ks | slabs << 11 | bits << 14 | flags << 18 | matrix << 22
+//   w = block index relative to the CTA's first block
+constexpr uint32_t DF_FLUSH = 1, DF_BLOCK_DONE = 2, DF_GPTQ = 4;
 
 struct I8Params {
     I8Mat mat[I8_MAX_MATS];
+    const uint4* plan_desc;           // stage descriptors, warp after warp, CTA after CTA
+    const uint32_t* plan_first;       // [ctas * warps + 1] first descriptor of every warp
+    const uint32_t* plan_cta;         // [ctas] first block | blocks << 16
     int num_mats, K, KS;
     const uint16_t* perm;             // stored row k' <- feature perm[k'], or NULL
     const half* x;
@@ -61,27 +71,25 @@ struct I8Params {
     float norm_eps;
     int mode, x_permuted;
     int ns;                           // weight ring slots per warp
-    int lcap;                         // capacity of a warp's stage list
-    int nb_max;                       // most blocks any CTA owns
+    int slot_bytes;                   // bytes of one ring slot (>= the largest stage)
+    int lcap;                         // most stages any warp has
     unsigned long long* dbg;          // optional globaltimer stamps (exl2b_debug_set), NULL in production
     int dbg_cta;
-    unsigned short cta_blk[I8_MAX_CTAS + 1];      // CTA c owns 32-column blocks [cta_blk[c], cta_blk[c+1]) of the launch
 };
 
 // dynamic shared-memory map of a CTA (byte offsets, every region 16-byte aligned) -- one definition for host and device
 struct I8Smem {
-    uint32_t act, asum, ascale, emit, list, blksrc, total;
+    uint32_t act, asum, ascale, emit, list, total;
 };
-__host__ __device__ inline I8Smem i8_smem_map(int warps, int ns, int KS, int lcap, int nb_max) {
+__host__ __device__ inline I8Smem i8_smem_map(int warps, int ns, int slot_bytes, int KS, int lcap) {
     auto up = [](uint32_t x) { return (x + 15u) & ~15u; };
     I8Smem m;
-    m.act = up((uint32_t)warps * (uint32_t)ns * I8_SLOT_BYTES);      // staged row: [KS][64 B]
+    m.act = up((uint32_t)warps * (uint32_t)ns * (uint32_t)slot_bytes);   // staged row: [KS][64 B]
     m.asum = up(m.act + (uint32_t)KS * 64u);                          // [KS] integer sum of a slab's row values
     m.ascale = up(m.asum + (uint32_t)KS * 4u);                        // [KS/4 + 1] scale of a 128-k block
     m.emit = up(m.ascale + (uint32_t)(KS / 4 + 1) * 4u);              // [warp][2][32] partial sums of split blocks
     m.list = up(m.emit + (uint32_t)warps * 256u);                     // [warp][lcap] stage descriptors
-    m.blksrc = up(m.list + (uint32_t)warps * (uint32_t)lcap * 8u);    // [nb_max] block streams
-    m.total = up(m.blksrc + (uint32_t)nb_max * 8u);
+    m.total = up(m.list + (uint32_t)warps * (uint32_t)lcap * 16u);
     return m;
 }
 
@@ -197,35 +205,12 @@ template <int BITS>
 __device__ __forceinline__ int consume_stage(uint32_t slot, int n, uint32_t xs, uint32_t asum, int lane, int (&am)[4], int (&ae)[2]) {
     constexpr uint32_t bb = 128 * BITS;
     int S = 0;
-#pragma unroll 2
+#pragma unroll 1
     for (int s = 0; s < n; ++s) {
         consume_slab<BITS>(slot + s * bb, xs + s * 64, lane, am, ae);
         S += (int)lds32(asum + s * 4);
     }
     return S;
-}
-
-// scale / zero-point of one (group, column), fetched a segment ahead of its use
-struct RawScale {
-    uint32_t w;        // EXL2: q_scale word of the lane's column;  GPTQ: qzeros word
-    half hs;           // GPTQ: fp16 scale;  EXL2: q_scale_max[group]
-};
-__device__ __forceinline__ RawScale load_scales(const I8Params& P, int mi, int blk, int group, int lane) {
-    const I8Mat& m = P.mat[mi];
-    const int n = (blk - m.blk_base) * 32 + lane;
-    RawScale r;
-    r.w = 0u;
-    r.hs = __ushort_as_half(0);
-    if (n < m.N) {
-        if (!m.is_gptq) {
-            r.w = __ldg(m.q_scale + (size_t)group * (m.N >> 3) + (n >> 3));
-            r.hs = __ldg(m.q_scale_max + group);
-        } else {
-            r.w = __ldg(m.qzeros + (size_t)group * (m.N >> 3) + (n >> 3));
-            r.hs = __ldg(m.gptq_scales + (size_t)group * m.N + n);
-        }
-    }
-    return r;
 }
 
 __device__ __forceinline__ void finalize_block(const I8Params& P, int blk, int lane, float v) {
@@ -258,15 +243,14 @@ __device__ __forceinline__ half gelu_h(half x) {        // cuda/q_mlp_activation
     return __float2half_rn(xf);
 }
 
-constexpr int DF_FLUSH = 1, DF_BLOCK_DONE = 2;
-
 __device__ __forceinline__ unsigned long long i8_gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 // stamps of thread 0 of CTA dbg_cta: 0 start, 1 first stages requested, 2 dependency wait over, 3 row staged,
-// 4 warp 0's main loop done, 5 all warps done, (6 = earliest CTA start, 7 = latest CTA end over the grid)
+// 4 warp 0's main loop done, 5 all warps done, (6 = earliest CTA start, 7 = latest CTA end over the grid), 8 stage list in
+// shared memory, 9 first stages and scales requested
 #define I8_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && tid == 0) P.dbg[i] = i8_gtimer(); if ((i) == 0 && tid == 0) atomicMin(P.dbg + 6, i8_gtimer()); } } while (0)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
@@ -287,110 +271,53 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     __syncthreads();
     griddep_launch_dependents();          // the next launch may become resident (and prefetch ITS weights) right away
 
-    // ---- this CTA's blocks / this warp's unit range (unit = (block, slab); CTA-relative linear index b * KS + ks)
-    const int blk0 = P.cta_blk[blockIdx.x], nb = (int)P.cta_blk[blockIdx.x + 1] - blk0;
-    if (nb <= 0) return;
-    const int units = nb * KS;
-    const int l0 = (units * warp) / I8_WARPS, l1 = (units * (warp + 1)) / I8_WARPS;
+    // ---- this CTA's blocks and this warp's stage list, straight from the host-built plan (nothing here depends on the
+    //      previous launch)
+    const uint32_t cinfo = __ldg(P.plan_cta + blockIdx.x);
+    const int blk0 = (int)(cinfo & 0xffffu), nb = (int)(cinfo >> 16);
+    const uint32_t f0 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp), f1 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp + 1);
+    const int nst = (int)(f1 - f0);
 
     // shared-memory map: generic pointers for the prologue's stores, 32-bit shared-space addresses (`lds*`) for the main loop
-    const I8Smem sm = i8_smem_map(I8_WARPS, ns, KS, P.lcap, P.nb_max);
+    const I8Smem sm = i8_smem_map(I8_WARPS, ns, P.slot_bytes, KS, P.lcap);
     uint8_t* const act_g = smem + sm.act;
     int* const asum_s = reinterpret_cast<int*>(smem + sm.asum);
     float* const ascale_s = reinterpret_cast<float*>(smem + sm.ascale);
     float* const emit_base = reinterpret_cast<float*>(smem + sm.emit);
-    uint2* const list_g = reinterpret_cast<uint2*>(smem + sm.list) + (size_t)warp * P.lcap;
-    unsigned long long* const blksrc_g = reinterpret_cast<unsigned long long*>(smem + sm.blksrc);
+    uint4* const list_g = reinterpret_cast<uint4*>(smem + sm.list) + (size_t)warp * P.lcap;
     uint32_t sbase;        // kept opaque: the compiler would otherwise re-derive every shared address from S2R in the loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_addr(smem)));
-    const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)(ns * I8_SLOT_BYTES);
+    const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)(ns * P.slot_bytes);
     const uint32_t act = sbase + sm.act, asum = sbase + sm.asum, ascale = sbase + sm.ascale;
-    const uint32_t list = sbase + sm.list + (uint32_t)warp * (uint32_t)P.lcap * 8u;
+    const uint32_t list = sbase + sm.list + (uint32_t)warp * (uint32_t)P.lcap * 16u;
     uint32_t bar0;
     asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_addr(&bars[warp * I8_MAX_STAGES])));
 
-    // per-block table: byte stream of block b (and its matrix, in the low 2 bits: streams are 16-byte aligned)
-    for (int b = tid; b < nb; b += I8_THREADS) {
-        const int blk = blk0 + b;
-        int mi = 0;
-#pragma unroll
-        for (int i = 1; i < I8_MAX_MATS; ++i)
-            if (i < P.num_mats && blk >= P.mat[i].blk_base) mi = i;
-        const I8Mat& m = P.mat[mi];
-        blksrc_g[b] = (unsigned long long)(m.packed + (size_t)(blk - m.blk_base) * m.blk_stream_bytes) | (unsigned long long)mi;
-    }
+    for (int i = lane; i < nst; i += 32) list_g[i] = __ldg(P.plan_desc + f0 + i);
+    __syncwarp();
+    I8_STAMP(8);
 
-    // ---- this warp's STAGE LIST, built here (nothing below depends on the previous launch): one 8-byte descriptor per stage
-    //        w0 = byte offset in the block stream | slabs << 22 | bits << 25 | flags << 29      w1 = ks | group << 11 | block << 22
-    //      so the main loop does no position arithmetic at all.  A stage is at most 2 KB (4 slabs up to 4 bits, 2 above) and
-    //      never crosses a quantisation group, a 128-k row block, a bit-width region or the end of the warp's range.
-    int nst = 0;
-    {
-        int lin = l0, b = l0 / KS, ks = l0 - (l0 / KS) * KS, mi = 0, r = 0;
-        auto set_block = [&]() {
-            const int blk = blk0 + b;
-            mi = 0;
-#pragma unroll
-            for (int i = 1; i < I8_MAX_MATS; ++i)
-                if (i < P.num_mats && blk >= P.mat[i].blk_base) mi = i;
-        };
-        int r_begin = 0, r_bits = 4, r_spg = 0, r_gbase = 0, r_end = 0;
-        uint32_t r_off = 0;
-        auto set_region = [&]() {
-            const I8Mat& m = P.mat[mi];
-            const QRegion& rg = m.reg[r];
-            r_begin = rg.ks_begin; r_bits = rg.bits; r_spg = rg.spg_log2; r_gbase = rg.group_base; r_off = rg.off_base;
-            r_end = (r + 1 < m.num_regions) ? m.reg[r + 1].ks_begin : KS;
-        };
-        if (lin < l1) {
-            set_block();
-            const I8Mat& m = P.mat[mi];
-#pragma unroll
-            for (int i = 1; i < MAX_REGIONS; ++i)
-                if (i < m.num_regions && ks >= m.reg[i].ks_begin) r = i;
-            set_region();
-        }
-        while (lin < l1) {
-            const int rel = ks - r_begin, g = rel >> r_spg;
-            const int gend = r_begin + ((g + 1) << r_spg);
-            const int segend = min(min(gend, (ks | 3) + 1), min(r_end, ks + (l1 - lin)));
-            const int n = min(segend - ks, r_bits > 4 ? 2 : 4);
-            const uint32_t flags = ((ks + n == segend) ? DF_FLUSH : 0) | ((ks + n == KS || lin + n == l1) ? DF_BLOCK_DONE : 0);
-            if (nst >= P.lcap) __trap();
-            if (lane == 0)
-                list_g[nst] = make_uint2((r_off + (uint32_t)(rel * 128 * r_bits)) | ((uint32_t)n << 22) | ((uint32_t)r_bits << 25) | (flags << 29),
-                                         (uint32_t)ks | ((uint32_t)(r_gbase + g) << 11) | ((uint32_t)b << 22));
-            ++nst;
-            lin += n;
-            ks += n;
-            if (ks >= KS) {
-                ks = 0;
-                ++b;
-                r = 0;
-                if (lin < l1) { set_block(); set_region(); }
-            } else if (ks >= r_end) {
-                ++r;
-                set_region();
-            }
-        }
-    }
-    __syncthreads();          // block table + stage lists visible
+    auto packed_of = [&](uint32_t mi) -> const uint8_t* { return mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed); };
+    auto wtab_of = [&](uint32_t mi) -> const void* { return mi == 0 ? P.mat[0].wtab : (mi == 1 ? P.mat[1].wtab : P.mat[2].wtab); };
     auto issue_stage = [&](int s, int slot_idx) {          // lane 0: request stage s into ring slot slot_idx
-        const uint2 d = lds64(list + (uint32_t)s * 8u);
-        const uint32_t bytes = ((d.x >> 22) & 7u) * 128u * ((d.x >> 25) & 15u);
-        const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (d.y >> 22));
+        const uint4 d = lds128(list + (uint32_t)s * 16u);
+        const uint32_t bytes = ((d.z >> 11) & 7u) * ((d.z >> 14) & 15u) * 128u;
         const uint32_t bar = bar0 + (uint32_t)slot_idx * 8u;
         mbar_arrive_expect_tx(bar, bytes);
-        bulk_copy_g2s(ring + (uint32_t)slot_idx * I8_SLOT_BYTES, reinterpret_cast<const uint8_t*>(src & ~3ull) + (d.x & 0x3fffffu), bytes, bar);
+        bulk_copy_g2s(ring + (uint32_t)(slot_idx * P.slot_bytes), packed_of((d.z >> 22) & 3u) + d.x, bytes, bar);
+    };
+    // scale (and GPTQ zero point) of the group a stage belongs to, for this lane's column
+    auto fetch_scale = [&](uint4 d) -> uint32_t {
+        const void* t = wtab_of((d.z >> 22) & 3u);
+        const uint32_t idx = d.y + (uint32_t)lane;
+        return (d.z & (DF_GPTQ << 18)) ? __ldg(reinterpret_cast<const uint32_t*>(t) + idx)
+                                        : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(t) + idx);
     };
     if (lane == 0)
         for (int i = 0; i < ns && i < nst; ++i) issue_stage(i, i);
-    RawScale raw = {0u, __ushort_as_half(0)};
-    if (nst > 0) {
-        const uint2 d0 = lds64(list);
-        const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (d0.y >> 22));
-        raw = load_scales(P, (int)(src & 3ull), blk0 + (int)(d0.y >> 22), (int)((d0.y >> 11) & 0x7ffu), lane);
-    }
+    uint32_t wraw = 0u;
+    if (nst > 0) wraw = fetch_scale(lds128(list));
+    I8_STAMP(9);
 
     // ---- static operands of the prologue, fetched before the dependency wait: permutation indices (when the row has to be
     //      gathered, or the norm weight has) and the norm weight of this thread's first octets
@@ -560,12 +487,13 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     float tot = 0.f;
     int S = 0, cslot = 0, blk_slabs = 0, emits = 0;
     uint32_t phase = 0;
+#pragma unroll 1
     for (int s = 0; s < nst; ++s) {
         mbar_wait(bar0 + (uint32_t)cslot * 8u, (phase >> cslot) & 1u);
         phase ^= 1u << cslot;
-        const uint2 d = lds64(list + (uint32_t)s * 8u);
-        const int n = (int)((d.x >> 22) & 7u), bits = (int)((d.x >> 25) & 15u), ks = (int)(d.y & 0x7ffu);
-        const uint32_t slot = ring + (uint32_t)cslot * I8_SLOT_BYTES;
+        const uint4 d = lds128(list + (uint32_t)s * 16u);
+        const int ks = (int)(d.z & 0x7ffu), n = (int)((d.z >> 11) & 7u), bits = (int)((d.z >> 14) & 15u);
+        const uint32_t slot = ring + (uint32_t)(cslot * P.slot_bytes);
         const uint32_t xs = act + (uint32_t)ks * 64u, as = asum + (uint32_t)ks * 4u;
         switch (bits) {
             case 4: S += consume_stage<4>(slot, n, xs, as, lane, am, ae); break;
@@ -579,41 +507,25 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         if (lane == 0 && s + ns < nst) issue_stage(s + ns, cslot);            // refill the slot just drained
         cslot = (cslot + 1 == ns) ? 0 : cslot + 1;
         blk_slabs += n;
-        if (d.x & ((uint32_t)DF_FLUSH << 29)) {
+        if (d.z & (DF_FLUSH << 18)) {
             // integer sums -> fp32:  sum_k a_k (q_k - zero) * scale  =  (sum a q - zero * sum a) * scale_w * scale_row
-            const int b = (int)(d.y >> 22);
-            const unsigned long long src = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + b);
-            const I8Mat& m = P.mat[(int)(src & 3ull)];
-            const int col = (blk0 + b - m.blk_base) * 32 + lane;
             int v = ((am[0] << 8) + am[1]) + (((am[2] << 8) + am[3]) >> 4) + (((ae[0] << 8) + ae[1]) << plane_main(bits));
-            const uint32_t nib = (raw.w >> ((col & 7) * 4)) & 15u;
-            float ws;
-            int zero;
-            if (!m.is_gptq) {
-                const int qs = (int)nib + 1;
-                ws = __half2float(__hmul(__int2half_rn(qs * qs), raw.hs));          // dq_scale, cuda/quant/qdq_util.cuh:24-30
-                zero = 1 << (bits - 1);
-            } else {
-                ws = __half2float(raw.hs);
-                zero = (int)nib + 1;                                                 // q_gemm_kernel_gptq.cuh:167-172
-            }
+            const float ws = __half2float(__ushort_as_half((unsigned short)(wraw & 0xffffu)));
+            const int zero = (d.z & (DF_GPTQ << 18)) ? (int)(wraw >> 16) : (1 << (bits - 1));
             v -= zero * S;
             tot = fmaf((float)v, ws * __uint_as_float(lds32(ascale + (uint32_t)(ks >> 2) * 4u)), tot);
             am[0] = am[1] = am[2] = am[3] = 0;
             ae[0] = ae[1] = 0;
             S = 0;
-            if (s + 1 < nst) {                 // scales of the next segment
-                const uint2 dn = lds64(list + (uint32_t)(s + 1) * 8u);
-                const unsigned long long sn = *reinterpret_cast<const volatile unsigned long long*>(blksrc_g + (dn.y >> 22));
-                raw = load_scales(P, (int)(sn & 3ull), blk0 + (int)(dn.y >> 22), (int)((dn.y >> 11) & 0x7ffu), lane);
-            }
-            if (d.x & ((uint32_t)DF_BLOCK_DONE << 29)) {
+            if (s + 1 < nst) wraw = fetch_scale(lds128(list + (uint32_t)(s + 1) * 16u));      // scales of the next group
+            if (d.z & (DF_BLOCK_DONE << 18)) {
+                const int blk = blk0 + (int)d.w;
                 if (blk_slabs == KS) {
-                    finalize_block(P, blk0 + b, lane, tot * rrms);          // this warp covered the block's whole K by itself
+                    finalize_block(P, blk, lane, tot * rrms);          // this warp covered the block's whole K by itself
                 } else {
                     if (emits >= 2) __trap();       // a warp's range has at most two partial blocks (its first and its last)
                     emit_base[(warp * 2 + emits) * 32 + lane] = tot;
-                    if (lane == 0) { em_blk[warp][emits] = blk0 + b; em_n[warp][emits] = blk_slabs; }
+                    if (lane == 0) { em_blk[warp][emits] = blk; em_n[warp][emits] = blk_slabs; }
                     ++emits;
                 }
                 tot = 0.f;
@@ -704,8 +616,114 @@ void i8_partition_blocks(const std::vector<uint32_t>& bytes, int ctas, unsigned 
     *used = c;
 }
 
+// ---- launch plans -------------------------------------------------------------------------------------------------------
+// Everything positional about a launch (block -> CTA partition, every warp's stage list) depends only on the STRUCTURE of its
+// matrices (K, N, bit-width regions, group sizes), not on their addresses: it is computed here once per structure, uploaded,
+// and shared by every launch with that structure (all 32 layers of a model use the same few plans, so the descriptors stay in
+// L2).  The kernel reads its list with one coalesced load per warp: no region walk, no divisions, no dynamic indexing of kernel
+// parameters on the device.
+struct I8Plan {
+    uint4* d_desc = nullptr;
+    uint32_t* d_first = nullptr;
+    uint32_t* d_cta = nullptr;
+    int ctas = 0, lcap = 0, slot_bytes = 0, max_bits = 0;
+};
+struct I8PlanMat {
+    int N, KS, is_gptq, num_regions;
+    uint32_t blk_stream_bytes;
+    QRegion reg[MAX_REGIONS];
+};
+static std::map<std::string, I8Plan> g_plans[64];
+static std::mutex g_plan_mutex;
+
+// stage lists of one launch structure: the same walk for every (CTA, warp) -- units are (block, slab) pairs, CTA-relative
+static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* cta_blk, int C, int warps, int slot_bytes,
+                           std::vector<uint4>& desc, std::vector<uint32_t>& first, std::vector<uint32_t>& cta, int* lcap) {
+    const int KS = mats[0].KS;
+    int blk_base[I8_MAX_MATS + 1] = {0};
+    for (int i = 0; i < nm; ++i) blk_base[i + 1] = blk_base[i] + (mats[i].N + 31) / 32;
+    *lcap = 1;
+    for (int c = 0; c < C; ++c) {
+        const int blk0 = cta_blk[c], nb = (int)cta_blk[c + 1] - blk0;
+        cta.push_back((uint32_t)blk0 | ((uint32_t)nb << 16));
+        const long long units = (long long)nb * KS;
+        for (int w = 0; w < warps; ++w) {
+            first.push_back((uint32_t)desc.size());
+            const int l0 = (int)((units * w) / warps), l1 = (int)((units * (w + 1)) / warps);
+            int lin = l0;
+            while (lin < l1) {
+                const int b = lin / KS, ks = lin - b * KS, blk = blk0 + b;
+                int mi = 0;
+                while (mi + 1 < nm && blk >= blk_base[mi + 1]) ++mi;
+                const I8PlanMat& m = mats[mi];
+                int r = 0;
+                while (r + 1 < m.num_regions && ks >= m.reg[r + 1].ks_begin) ++r;
+                const QRegion& rg = m.reg[r];
+                const int r_end = (r + 1 < m.num_regions) ? m.reg[r + 1].ks_begin : KS;
+                const int rel = ks - rg.ks_begin, g = rel >> rg.spg_log2;
+                const int gend = rg.ks_begin + ((g + 1) << rg.spg_log2);
+                // a stage never crosses a quantisation group, a 128-k row block, a bit-width region or the end of the warp's range
+                const int segend = std::min(std::min(gend, (ks | 3) + 1), std::min(r_end, ks + (l1 - lin)));
+                const int len = segend - ks, cap = std::max(1, std::min(4, slot_bytes / (128 * rg.bits)));
+                const int pieces = (len + cap - 1) / cap, n = (len + pieces - 1) / pieces;
+                uint32_t flags = (ks + n == segend ? DF_FLUSH : 0u) | ((ks + n == KS || lin + n == l1) ? DF_BLOCK_DONE : 0u) | (m.is_gptq ? DF_GPTQ : 0u);
+                if (flags & DF_BLOCK_DONE) flags |= DF_FLUSH;
+                const int bim = blk - blk_base[mi];
+                uint4 d;
+                d.x = (uint32_t)bim * m.blk_stream_bytes + rg.off_base + (uint32_t)rel * 128u * (uint32_t)rg.bits;
+                d.y = (uint32_t)(rg.group_base + g) * (uint32_t)m.N + (uint32_t)bim * 32u;
+                d.z = (uint32_t)ks | ((uint32_t)n << 11) | ((uint32_t)rg.bits << 14) | (flags << 18) | ((uint32_t)mi << 22);
+                d.w = (uint32_t)b;
+                desc.push_back(d);
+                lin += n;
+            }
+            *lcap = std::max(*lcap, (int)(desc.size() - first.back()));
+        }
+    }
+    first.push_back((uint32_t)desc.size());
+}
+
+static int i8_get_plan(int device, const I8PlanMat* mats, int nm, int sms, int warps, I8Plan* out) {
+    std::string key((const char*)mats, sizeof(I8PlanMat) * nm);
+    const int extra[3] = {nm, sms, warps};
+    key.append((const char*)extra, sizeof(extra));
+    std::lock_guard<std::mutex> lk(g_plan_mutex);
+    auto it = g_plans[device].find(key);
+    if (it != g_plans[device].end()) { *out = it->second; return 0; }
+
+    I8Plan pl;
+    std::vector<uint32_t> blk_bytes;
+    for (int i = 0; i < nm; ++i) {
+        // only blocks that hold real columns (the last strip of a padded matrix may contain all-padding blocks)
+        for (int b = 0; b < (mats[i].N + 31) / 32; ++b) blk_bytes.push_back(mats[i].blk_stream_bytes);
+        for (int r = 0; r < mats[i].num_regions; ++r) pl.max_bits = std::max(pl.max_bits, mats[i].reg[r].bits);
+    }
+    EXL2B_REQUIRE(blk_bytes.size() < 65535, "too many column blocks (%zu)", blk_bytes.size());
+    EXL2B_REQUIRE((long long)blk_bytes.size() * mats[0].KS < (1ll << 30), "problem too large for 32-bit unit arithmetic");
+    unsigned short cta_blk[I8_MAX_CTAS + 1];
+    i8_partition_blocks(blk_bytes, sms, cta_blk, &pl.ctas);
+    // ring slot: 2 KB holds 4 slabs up to 4 bits; wider planes get 3 KB slots (4 slabs at 5 / 6 bits, 3 at 8)
+    static const int slot_override = [] { const char* e = getenv("EXL2B_I8_SLOT"); return e ? atoi(e) : 0; }();
+    pl.slot_bytes = slot_override ? slot_override : (pl.max_bits > 4 ? 3072 : 2048);
+    std::vector<uint4> desc;
+    std::vector<uint32_t> first, cta;
+    i8_build_lists(mats, nm, cta_blk, pl.ctas, warps, pl.slot_bytes, desc, first, cta, &pl.lcap);
+    EXL2B_CUDA(cudaMalloc(&pl.d_desc, desc.size() * sizeof(uint4) + 16));
+    EXL2B_CUDA(cudaMalloc(&pl.d_first, first.size() * 4));
+    EXL2B_CUDA(cudaMalloc(&pl.d_cta, cta.size() * 4));
+    EXL2B_CUDA(cudaMemcpy(pl.d_desc, desc.data(), desc.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    EXL2B_CUDA(cudaMemcpy(pl.d_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+    EXL2B_CUDA(cudaMemcpy(pl.d_cta, cta.data(), cta.size() * 4, cudaMemcpyHostToDevice));
+    g_plans[device][key] = pl;
+    *out = pl;
+    return 0;
+}
+
+// A launch structure is planned (cudaMalloc + synchronous upload) the first time it is seen: never inside a stream capture --
+// run every shape once eagerly first, as model.capture() does.
 int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, const I8Input& in) {
     EXL2B_REQUIRE(nm >= 1 && nm <= I8_MAX_MATS, "bad matrix count %d", nm);
+    EXL2B_REQUIRE(device >= 0 && device < 64, "bad device %d", device);
     EXL2B_REQUIRE(in.x, "null input row");
     EXL2B_REQUIRE(in.mode != I8_RMSNORM || in.norm_w, "RMSNorm prologue without a weight");
     EXL2B_REQUIRE((in.mode != I8_SILU_MUL && in.mode != I8_GELU_MUL) || in.x2, "act*mul prologue without the second operand");
@@ -716,7 +734,7 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
         return (w == 12 || w == 8) ? w : 16;
     }();
     static bool attr_set[64] = {false};
-    if (device >= 0 && device < 64 && !attr_set[device]) {
+    if (!attr_set[device]) {
         EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         EXL2B_CUDA(cudaFuncSetAttribute(gemv_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -734,7 +752,8 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.norm_eps = in.norm_eps;
     P.mode = in.mode;
     P.x_permuted = in.x_permuted;
-    std::vector<uint32_t> blk_bytes;
+    I8PlanMat pm[I8_MAX_MATS];
+    memset(pm, 0, sizeof(pm));
     int blk = 0;
     for (int i = 0; i < nm; ++i) {
         const QMatrix* q = outs[i].q;
@@ -743,50 +762,37 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
         EXL2B_REQUIRE(v.layout == LAYOUT_TC, "matrix is not in the tcgen05 layout");
         EXL2B_REQUIRE(v.KS == P.KS, "fused matrices must share K");
         EXL2B_REQUIRE((v.perm == nullptr) == (P.perm == nullptr), "fused matrices must share their row permutation");
+        EXL2B_REQUIRE(q->wtab, "matrix has no scale table");
+        EXL2B_REQUIRE(q->packed_bytes < (1ull << 32), "matrix too large for 32-bit stage offsets");
         I8Mat& m = P.mat[i];
         m.packed = reinterpret_cast<const uint8_t*>(v.packed);
-        m.q_scale = v.q_scale;
-        m.q_scale_max = v.q_scale_max;
-        m.qzeros = v.qzeros;
-        m.gptq_scales = v.gptq_scales;
+        m.wtab = q->wtab;
         m.bias = v.bias;
         m.c = outs[i].c;
         m.c_perm = outs[i].c_perm;
         m.out_invperm = outs[i].out_invperm;
         m.clear = outs[i].clear;
-        m.blk_stream_bytes = v.blk_stream_bytes;
         m.N = v.N;
         m.blk_base = blk;
-        m.is_gptq = v.is_gptq;
-        m.num_regions = v.num_regions;
-        for (int r = 0; r < v.num_regions; ++r) m.reg[r] = v.reg[r];
-        // only blocks that hold real columns (the last strip of a padded matrix may contain all-padding blocks)
-        const int nblk = (v.N + 31) / 32;
-        for (int b = 0; b < nblk; ++b) blk_bytes.push_back(v.blk_stream_bytes);
-        blk += nblk;
+        blk += (v.N + 31) / 32;
+        pm[i].N = v.N;
+        pm[i].KS = v.KS;
+        pm[i].is_gptq = v.is_gptq;
+        pm[i].num_regions = v.num_regions;
+        pm[i].blk_stream_bytes = v.blk_stream_bytes;
+        for (int r = 0; r < v.num_regions; ++r) pm[i].reg[r] = v.reg[r];
     }
-    EXL2B_REQUIRE(blk < 65535, "too many column blocks (%d)", blk);
-    EXL2B_REQUIRE((long long)blk * P.KS < (1ll << 26), "problem too large for 32-bit unit arithmetic");
-    const int sms = std::min(device_sm_count(device), I8_MAX_CTAS);
-    int C = 0;
-    i8_partition_blocks(blk_bytes, sms, P.cta_blk, &C);
+    EXL2B_REQUIRE(P.KS <= 2048, "K = %d exceeds the stage descriptor (K <= 65536)", P.K);
+    I8Plan pl;
+    int rc = i8_get_plan(device, pm, nm, std::min(device_sm_count(device), I8_MAX_CTAS), warps, &pl);
+    if (rc) return rc;
+    P.plan_desc = pl.d_desc;
+    P.plan_first = pl.d_first;
+    P.plan_cta = pl.d_cta;
+    P.lcap = pl.lcap;
+    P.slot_bytes = pl.slot_bytes;
 
-    // shared memory: i8_smem_map (weight rings, staged row, per-warp partials, stage lists, block table)
-    // stage-list capacity: an upper bound of the stages one warp can have (every boundary a stage may not cross adds at most one)
-    int nb_max = 0, smin = 4, max_regions = 1;
-    for (int c = 0; c < C; ++c) nb_max = std::max(nb_max, (int)P.cta_blk[c + 1] - (int)P.cta_blk[c]);
-    for (int i = 0; i < nm; ++i) {
-        max_regions = std::max(max_regions, P.mat[i].num_regions);
-        for (int r = 0; r < P.mat[i].num_regions; ++r) {
-            smin = std::min(smin, std::min(1 << P.mat[i].reg[r].spg_log2, P.mat[i].reg[r].bits > 4 ? 2 : 4));
-            if (P.mat[i].reg[r].ks_begin & 3) smin = 1;      // groups not aligned with the 128-k row blocks: segments may be single slabs
-        }
-    }
-    const int upw = (nb_max * P.KS + warps - 1) / warps + 1;
-    P.lcap = (upw + smin - 1) / smin + (upw / P.KS + 2) * (max_regions + 1) + 4;
-    P.nb_max = nb_max;
-    EXL2B_REQUIRE(P.KS <= 2048 && nb_max < 1024, "matrix too large for the stage descriptor (K <= 65536)");
-    auto smem_for = [&](int ns) { return (size_t)i8_smem_map(warps, ns, P.KS, P.lcap, P.nb_max).total; };
+    auto smem_for = [&](int ns) { return (size_t)i8_smem_map(warps, ns, P.slot_bytes, P.KS, P.lcap).total; };
     // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: the deepest ring
     // (<= 4 slots per warp) that keeps the CTA <= 112 KB, never fewer than 2 slots
     P.ns = I8_MAX_STAGES;
@@ -799,6 +805,7 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     extern int g_dbg_cta, g_dbg_slot;
     P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
+    const int C = pl.ctas;
     if (warps == 16) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
     else if (warps == 12) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
     else EXL2B_CUDA(launch_pdl(gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
@@ -812,5 +819,30 @@ extern "C" int exl2b_debug_partition(const uint32_t* block_bytes, int num_blocks
     EXL2B_REQUIRE(block_bytes && out && used && num_blocks > 0 && ctas > 0 && ctas <= exl2b::I8_MAX_CTAS, "bad argument");
     std::vector<uint32_t> b(block_bytes, block_bytes + num_blocks);
     exl2b::i8_partition_blocks(b, ctas, out, used);
+    return 0;
+}
+
+// host-only diagnostics hook (tests/test_i8_emulation.py): the stage lists gemv_i8_launch would use for ONE matrix with the
+// given regions (5 ints each: ks_begin, bits, spg_log2, group_base, off_base).  desc: capacity cap_desc x 4 words; first:
+// ctas * warps + 1 words; returns the CTA count in *ctas_used, the descriptor count in *n_desc.
+extern "C" int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_bytes, const int* regions, int num_regions, int ctas, int warps,
+                                int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap) {
+    EXL2B_REQUIRE(regions && desc && first && ctas_used && n_desc && lcap, "null argument");
+    EXL2B_REQUIRE(num_regions >= 1 && num_regions <= exl2b::MAX_REGIONS && ctas > 0 && ctas <= exl2b::I8_MAX_CTAS && warps > 0, "bad argument");
+    exl2b::I8PlanMat m;
+    memset(&m, 0, sizeof(m));
+    m.N = N; m.KS = KS; m.is_gptq = is_gptq; m.num_regions = num_regions; m.blk_stream_bytes = blk_stream_bytes;
+    for (int r = 0; r < num_regions; ++r)
+        m.reg[r] = exl2b::QRegion{regions[5 * r], regions[5 * r + 1], regions[5 * r + 2], regions[5 * r + 3], (uint32_t)regions[5 * r + 4]};
+    std::vector<uint32_t> bb((N + 31) / 32, blk_stream_bytes);
+    unsigned short cta_blk[exl2b::I8_MAX_CTAS + 1];
+    exl2b::i8_partition_blocks(bb, ctas, cta_blk, ctas_used);
+    std::vector<uint4> d;
+    std::vector<uint32_t> f, c;
+    exl2b::i8_build_lists(&m, 1, cta_blk, *ctas_used, warps, slot_bytes, d, f, c, lcap);
+    EXL2B_REQUIRE((int)d.size() <= cap_desc, "descriptor buffer too small (%zu)", d.size());
+    memcpy(desc, d.data(), d.size() * sizeof(uint4));
+    memcpy(first, f.data(), f.size() * 4);
+    *n_desc = (int)d.size();
     return 0;
 }

@@ -146,6 +146,23 @@ __device__ void reconstruct_block_exl2(const QMatView& v, const uint32_t* bp, in
     }
 }
 
+// Dense scale table of the batch-1 GEMV: one entry per (group, column), natural column order, so that its per-group flush is
+// one coalesced load per warp with no nibble extraction / region lookup (EXL2: the exact fp16 dq_scale of
+// cuda/quant/qdq_util.cuh:24-30; GPTQ: the checkpoint's fp16 scale and qzero + 1 of q_gemm_kernel_gptq.cuh:167-172).
+__global__ void scale_table_kernel(QMatView v, void* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)v.groups * v.N) return;
+    const int g = (int)(idx / v.N), n = (int)(idx - (size_t)g * v.N);
+    if (!v.is_gptq) {
+        const uint32_t word = v.q_scale[(size_t)g * (v.N / 8) + (n >> 3)];
+        reinterpret_cast<half*>(out)[idx] = exl2_scale_h((word >> ((n & 7) * 4)) & 15u, v.q_scale_max[g]);
+    } else {
+        const uint32_t word = v.qzeros[(size_t)g * (v.N / 8) + (n >> 3)];
+        const uint32_t zero = ((word >> ((n & 7) * 4)) & 15u) + 1u;
+        reinterpret_cast<uint32_t*>(out)[idx] = (uint32_t)__half_as_ushort(v.gptq_scales[idx]) | (zero << 16);
+    }
+}
+
 // out[row * ld + (n - col0)] for the strips [strip0, strip0 + gridDim.y): the whole matrix (ld = N, col0 = 0, strip0 = 0) for
 // exl2b_reconstruct, or a column window for the large-M path (gemm_big.cu)
 __global__ void reconstruct_kernel(QMatView v, int gptq_groupsize, half* __restrict__ out, int ld, int col0, int strip0) {
@@ -439,6 +456,15 @@ extern "C" int exl2b_qmatrix_create(const exl2b_qmatrix_desc* d, exl2b_stream_t 
         cudaFree(m->tables);
         return fail(-1);
     }
+    {   // dense scale table (+64 B: the padding lanes of a last partial block read past the last row)
+        const size_t entries = (size_t)v.groups * v.N, wbytes = entries * (is_gptq ? 4 : 2) + 128;
+        if (cudaMalloc(&m->wtab, wbytes) != cudaSuccess) { set_error("CUDA out of memory (scale table)"); cudaFree(m->tables); return fail(-3); }
+        cudaMemsetAsync(m->wtab, 0, wbytes, stream);
+        scale_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, stream>>>(v, m->wtab);
+        g_launch_count++;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error("scale table failed: %s", cudaGetErrorString(e)); cudaFree(m->tables); cudaFree(m->wtab); return fail(-1); }
+    }
     *out = (exl2b_qmatrix_t)m;
     return 0;
 }
@@ -462,6 +488,7 @@ extern "C" int exl2b_qmatrix_destroy(exl2b_qmatrix_t h) {
     cudaSetDevice(m->device);
     if (m->tables) cudaFree(m->tables);
     if (m->owned_packed) cudaFree(m->owned_packed);
+    if (m->wtab) cudaFree(m->wtab);
     if (m->xp_buf) cudaFree(m->xp_buf);
     if (m->sumsq_buf) cudaFree(m->sumsq_buf);
     delete m;

@@ -222,3 +222,89 @@ def test_block_partition(name, bb, ctas):
     else:
         # uniform-ish blocks: never more than one block above the ideal share
         assert worst <= -(-total // ctas) + biggest
+
+
+# ---- stage lists -----------------------------------------------------------------------------------------------------------
+# gemv_i8.cu i8_build_lists (host): every (block, slab) unit of the launch appears in exactly one stage of exactly one warp, in
+# order; a stage never crosses a quantisation group, a 128-k row block, a bit-width region, and fits the ring slot; the flush
+# flag closes every group / row block / range, the block-done flag the warp's share of a block.
+
+
+def _plan(N, KS, regions, ctas=148, warps=16, slot=3072, gptq=0):
+    import ctypes
+
+    from exllamav2_b200 import ext as ext_c
+    f = ext_c.lib.exl2b_debug_plan
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                  ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    # regions: (ks_begin, bits, spg_log2); group_base / off_base derived like qmatrix.cu build_regions
+    reg, gbase, off = [], 0, 0
+    for i, (ks0, bits, lg) in enumerate(regions):
+        ks1 = regions[i + 1][0] if i + 1 < len(regions) else KS
+        reg += [ks0, bits, lg, gbase, off]
+        gbase += -(-(ks1 - ks0) // (1 << lg))
+        off += (ks1 - ks0) * 128 * bits
+    stream_bytes = off
+    ra = np.asarray(reg, dtype=np.int32)
+    cap = ((N + 31) // 32) * KS + 148 * 16 * 8
+    desc = np.zeros((cap, 4), dtype=np.uint32)
+    first = np.zeros(ctas * warps + 2, dtype=np.uint32)
+    used, nd, lcap = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    rc = f(N, KS, gptq, stream_bytes, ra.ctypes.data, len(regions), ctas, warps, slot, desc.ctypes.data, cap, first.ctypes.data,
+           ctypes.byref(used), ctypes.byref(nd), ctypes.byref(lcap))
+    assert rc == 0
+    return desc[: nd.value], first[: used.value * warps + 1], used.value, lcap.value, stream_bytes, reg
+
+
+PLAN_CASES = [
+    ("4096x4096 [5,4] g128", 4096, 128, [(0, 5, 2), (13, 4, 2)]),
+    ("11008 cols [4,3] g128", 11008, 128, [(0, 4, 2), (13, 3, 2)]),
+    ("K=11008 [5,4]", 4096, 344, [(0, 5, 2), (36, 4, 2)]),
+    ("head 6-bit", 32000, 128, [(0, 6, 2)]),
+    ("8-bit g32 + 2-bit g64", 512, 64, [(0, 8, 0), (5, 2, 1)]),
+    ("g256", 1024, 64, [(0, 4, 3)]),
+    ("ragged columns", 1000, 16, [(0, 3, 0), (3, 2, 2)]),
+]
+
+
+@pytest.mark.parametrize("name,N,KS,regions", PLAN_CASES, ids=[c[0] for c in PLAN_CASES])
+@pytest.mark.parametrize("warps,slot", [(16, 3072), (12, 2048)])
+def test_stage_lists(name, N, KS, regions, warps, slot):
+    desc, first, C, lcap, stream_bytes, reg = _plan(N, KS, regions, warps=warps, slot=slot)
+    nblk = (N + 31) // 32
+    seen = np.zeros((nblk, KS), dtype=np.int32)
+    assert first[0] == 0 and first[-1] == len(desc) and np.all(np.diff(first.astype(np.int64)) >= 0)
+    assert lcap == int(np.max(np.diff(first.astype(np.int64))))
+    # CTA block ranges: recover from the partition hook (same inputs)
+    bounds, used = _partition([stream_bytes] * nblk, 148)
+    assert used == C
+    ends = {r[0]: (regions[i + 1][0] if i + 1 < len(regions) else KS) for i, r in enumerate(regions)}
+    for c in range(C):
+        for w in range(warps):
+            lst = desc[first[c * warps + w]: first[c * warps + w + 1]]
+            prev = None
+            for i, (x, y, z, bw) in enumerate(lst):
+                ks, n, bits, flags, mi = z & 0x7FF, (z >> 11) & 7, (z >> 14) & 15, (z >> 18) & 15, (z >> 22) & 3
+                blk = bounds[c] + int(bw)
+                assert mi == 0 and 1 <= n <= 4 and n * bits * 128 <= slot
+                r = max(j for j, rg in enumerate(regions) if ks >= rg[0])
+                ks0, rb, lg = regions[r]
+                assert bits == rb and ks + n <= ends[ks0], "one region"
+                assert (ks >> 2) == ((ks + n - 1) >> 2), "one 128-k row block"
+                g0, g1 = (ks - ks0) >> lg, (ks + n - 1 - ks0) >> lg
+                assert g0 == g1, "one group"
+                assert x == blk * stream_bytes + reg[5 * r + 4] + (ks - ks0) * 128 * bits
+                assert y == (reg[5 * r + 3] + g0) * N + blk * 32
+                seen[blk, ks:ks + n] += 1
+                cur = (blk, ks)
+                if prev is not None:
+                    assert cur == (prev[0], prev[1]) or cur == (prev[0] + 1, 0), "contiguous walk"
+                prev = (blk, ks + n) if ks + n < KS else (blk + 1, 0)
+                last = i + 1 == len(lst)
+                nxt = lst[i + 1] if not last else None
+                group_closes = last or ks + n == KS or ((ks + n) & 3) == 0 or ks + n == ends[ks0] or ((ks + n - ks0) >> lg) != g0
+                assert bool(flags & 1) == group_closes, "flush flag"
+                assert bool(flags & 2) == (last or ks + n == KS), "block-done flag"
+                assert not (flags & 4)
+    assert np.all(seen == 1), "every (block, slab) exactly once"
