@@ -17,6 +17,7 @@ int g_tc_ctas_per_sm = [] { const char* e = getenv("EXL2B_TC_CTAS"); return e ? 
 unsigned long long* g_dbg = nullptr;
 int g_dbg_cta = 0;
 int g_dbg_slot = 0;
+unsigned long long* g_dbg_rec = nullptr;      // optional per-CTA records of the batch-1 GEMV: [64 launches][160 CTAs][4]
 
 // Split-K workspace, arrival counters and the activation-operand scratch of the tcgen05 kernel, one set per (device, stream):
 // launches on different streams (or host threads driving different streams) never share scratch.  Created on first use --
@@ -138,5 +139,9 @@ extern "C" int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int 
     exl2b::g_dbg = stamps;
     exl2b::g_dbg_cta = cta;
     exl2b::g_dbg_slot = 0;
+    return 0;
+}
+extern "C" int exl2b_debug_set_records(unsigned long long* records) {
+    exl2b::g_dbg_rec = records;
     return 0;
 }

@@ -37,7 +37,6 @@
 namespace exl2b {
 
 constexpr int I8_MAX_WARPS = 16;
-constexpr int I8_MAX_STAGES = 4;
 constexpr int I8_MAX_CTAS = 160;
 
 struct I8Mat {
@@ -55,13 +54,18 @@ struct I8Mat {
 //   x = byte offset of the stage inside its matrix' packed buffer
 //   y = element index of lane 0's entry in the matrix' scale table (group * N + first column of the block)
 //   z = ks | slabs << 11 | bits << 14 | flags << 18 | matrix << 22
-//   w = block index relative to the CTA's first block
+//   w = block index relative to the CTA's first block | (byte offset of the stage in the warp's arena / 128) << 16
+//       | (stages to request once this one is consumed) << 24
+// A warp's weight arena is a byte ring (not fixed slots): the host places every stage, records after which stage's consumption its
+// space is free (that is the `request` count above), and the first stages -- everything that fits the arena, for small matrices the
+// warp's WHOLE share -- are requested before the dependency wait.  Stage s completes on mbarrier s % I8_BARS, parity (s / I8_BARS) & 1.
 constexpr uint32_t DF_FLUSH = 1, DF_BLOCK_DONE = 2, DF_GPTQ = 4;
+constexpr int I8_BARS = 8;
 
 struct I8Params {
     I8Mat mat[I8_MAX_MATS];
     const uint4* plan_desc;           // stage descriptors, warp after warp, CTA after CTA
-    const uint32_t* plan_first;       // [ctas * warps + 1] first descriptor of every warp
+    const uint32_t* plan_first;       // [ctas * warps + 1] first descriptor of every warp | stages to request up front << 26
     const uint32_t* plan_cta;         // [ctas] first block | blocks << 16
     int num_mats, K, KS;
     const uint16_t* perm;             // stored row k' <- feature perm[k'], or NULL
@@ -70,21 +74,21 @@ struct I8Params {
     const half* norm_w;
     float norm_eps;
     int mode, x_permuted;
-    int ns;                           // weight ring slots per warp
-    int slot_bytes;                   // bytes of one ring slot (>= the largest stage)
+    int arena;                        // bytes of a warp's weight arena
     int lcap;                         // most stages any warp has
     unsigned long long* dbg;          // optional globaltimer stamps (exl2b_debug_set), NULL in production
     int dbg_cta;
+    unsigned long long* dbg_rec;      // optional per-CTA records [cta][4]: start, dependency wait over, end, SM id
 };
 
 // dynamic shared-memory map of a CTA (byte offsets, every region 16-byte aligned) -- one definition for host and device
 struct I8Smem {
     uint32_t act, asum, ascale, emit, list, total;
 };
-__host__ __device__ inline I8Smem i8_smem_map(int warps, int ns, int slot_bytes, int KS, int lcap) {
+__host__ __device__ inline I8Smem i8_smem_map(int warps, int arena, int KS, int lcap) {
     auto up = [](uint32_t x) { return (x + 15u) & ~15u; };
     I8Smem m;
-    m.act = up((uint32_t)warps * (uint32_t)ns * (uint32_t)slot_bytes);   // staged row: [KS][64 B]
+    m.act = up((uint32_t)warps * (uint32_t)arena);                   // staged row: [KS][64 B]
     m.asum = up(m.act + (uint32_t)KS * 64u);                          // [KS] integer sum of a slab's row values
     m.ascale = up(m.asum + (uint32_t)KS * 4u);                        // [KS/4 + 1] scale of a 128-k block
     m.emit = up(m.ascale + (uint32_t)(KS / 4 + 1) * 4u);              // [warp][2][32] partial sums of split blocks
@@ -258,14 +262,15 @@ template <int I8_WARPS>
 __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_constant__ I8Params P) {
     constexpr int I8_THREADS = I8_WARPS * 32;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bars[I8_WARPS * I8_MAX_STAGES];
+    __shared__ uint64_t bars[I8_WARPS * I8_BARS];
     __shared__ float s_red[I8_WARPS];
     __shared__ int em_blk[I8_WARPS][2], em_n[I8_WARPS][2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KS = P.KS, ns = P.ns;
+    const int KS = P.KS;
     I8_STAMP(0);
-    if (tid < I8_WARPS * I8_MAX_STAGES) mbar_init(smem_addr(&bars[tid]), 1);
+    if (P.dbg_rec && tid == 0) P.dbg_rec[blockIdx.x * 4] = i8_gtimer();
+    if (tid < I8_WARPS * I8_BARS) mbar_init(smem_addr(&bars[tid]), 1);
     if (tid < I8_WARPS * 2) em_blk[tid >> 1][tid & 1] = -1;
     mbar_fence_init();
     __syncthreads();
@@ -275,11 +280,12 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     //      previous launch)
     const uint32_t cinfo = __ldg(P.plan_cta + blockIdx.x);
     const int blk0 = (int)(cinfo & 0xffffu), nb = (int)(cinfo >> 16);
-    const uint32_t f0 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp), f1 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp + 1);
-    const int nst = (int)(f1 - f0);
+    const uint32_t fw0 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp), fw1 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp + 1);
+    const uint32_t f0 = fw0 & 0x3ffffffu, f1 = fw1 & 0x3ffffffu;
+    const int nst = (int)(f1 - f0), n_pre = (int)(fw0 >> 26);
 
     // shared-memory map: generic pointers for the prologue's stores, 32-bit shared-space addresses (`lds*`) for the main loop
-    const I8Smem sm = i8_smem_map(I8_WARPS, ns, P.slot_bytes, KS, P.lcap);
+    const I8Smem sm = i8_smem_map(I8_WARPS, P.arena, KS, P.lcap);
     uint8_t* const act_g = smem + sm.act;
     int* const asum_s = reinterpret_cast<int*>(smem + sm.asum);
     float* const ascale_s = reinterpret_cast<float*>(smem + sm.ascale);
@@ -287,11 +293,11 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     uint4* const list_g = reinterpret_cast<uint4*>(smem + sm.list) + (size_t)warp * P.lcap;
     uint32_t sbase;        // kept opaque: the compiler would otherwise re-derive every shared address from S2R in the loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_addr(smem)));
-    const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)(ns * P.slot_bytes);
+    const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)P.arena;
     const uint32_t act = sbase + sm.act, asum = sbase + sm.asum, ascale = sbase + sm.ascale;
     const uint32_t list = sbase + sm.list + (uint32_t)warp * (uint32_t)P.lcap * 16u;
     uint32_t bar0;
-    asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_addr(&bars[warp * I8_MAX_STAGES])));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_addr(&bars[warp * I8_BARS])));
 
     for (int i = lane; i < nst; i += 32) list_g[i] = __ldg(P.plan_desc + f0 + i);
     __syncwarp();
@@ -299,12 +305,12 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
 
     auto packed_of = [&](uint32_t mi) -> const uint8_t* { return mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed); };
     auto wtab_of = [&](uint32_t mi) -> const void* { return mi == 0 ? P.mat[0].wtab : (mi == 1 ? P.mat[1].wtab : P.mat[2].wtab); };
-    auto issue_stage = [&](int s, int slot_idx) {          // lane 0: request stage s into ring slot slot_idx
+    auto issue_stage = [&](int s) {          // lane 0: request stage s into its place in the arena
         const uint4 d = lds128(list + (uint32_t)s * 16u);
         const uint32_t bytes = ((d.z >> 11) & 7u) * ((d.z >> 14) & 15u) * 128u;
-        const uint32_t bar = bar0 + (uint32_t)slot_idx * 8u;
+        const uint32_t bar = bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u;
         mbar_arrive_expect_tx(bar, bytes);
-        bulk_copy_g2s(ring + (uint32_t)(slot_idx * P.slot_bytes), packed_of((d.z >> 22) & 3u) + d.x, bytes, bar);
+        bulk_copy_g2s(ring + ((d.w >> 16) & 0xffu) * 128u, packed_of((d.z >> 22) & 3u) + d.x, bytes, bar);
     };
     // scale (and GPTQ zero point) of the group a stage belongs to, for this lane's column
     auto fetch_scale = [&](uint4 d) -> uint32_t {
@@ -314,7 +320,8 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
                                         : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(t) + idx);
     };
     if (lane == 0)
-        for (int i = 0; i < ns && i < nst; ++i) issue_stage(i, i);
+        for (int i = 0; i < n_pre; ++i) issue_stage(i);
+    int next_req = n_pre;
     uint32_t wraw = 0u;
     if (nst > 0) wraw = fetch_scale(lds128(list));
     I8_STAMP(9);
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     I8_STAMP(1);
     griddep_wait();                        // everything below may read what the previous launch wrote
     I8_STAMP(2);
+    if (P.dbg_rec && tid == 0) P.dbg_rec[blockIdx.x * 4 + 1] = i8_gtimer();
 
     // ---- prologue: the row -> (optional RMSNorm weight / act*mul) -> 16-bit integers per 128-k block -> shared memory.
     //      Every CTA stages the whole row (its blocks span all of K); 1/rms is applied to the finished fp32 sums.
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
                 const half* wh = reinterpret_cast<const half*>(&wreg);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float xf = fmaxf(-65504.f, fminf(__half2float(h[e]), 65504.f));
+                    const float xf = __half2float(h[e]);
                     sumsq = fmaf(xf, xf, sumsq);
                     f[e] = xf * __half2float(wh[e]);
                 }
@@ -423,23 +431,29 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
 #pragma unroll
         for (int s = 1; s < 16; s <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));      // 16 lanes = one 128-k block
         // power-of-two block scale 2^e with max * 2^e in [2^14, 2^15): fp16 row values within a factor 16 of the block maximum
-        // are represented EXACTLY and all scale products are exact -- a unit-vector row returns reconstruct()'s fp16 weights
-        const uint32_t ef = (__float_as_uint(amax) >> 23) & 0xffu;
+        // are represented EXACTLY and all scale products are exact -- a unit-vector row returns reconstruct()'s fp16 weights.
+        // (the exponent is taken from max * (1 + 2^-15): a maximum that would round up to 2^15 gets the next scale instead)
+        const uint32_t ef = (__float_as_uint(amax * 1.000030518f) >> 23) & 0xffu;
         const float inv = amax > 0.f ? __uint_as_float((268u - ef) << 23) : 0.f;
-        int q[8], sum = 0;
+        // round to nearest even through the fp32 adder: bits(x * inv + 1.5 * 2^23) = 0x4B400000 + q, the low 16 bits are q as int16
+        uint32_t qb[8], usum = 0u;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { q[e] = __float2int_rn(f[e] * inv); sum += q[e]; }
+        for (int e = 0; e < 8; ++e) {
+            qb[e] = __float_as_uint(fmaf(f[e], inv, 12582912.f));
+            usum += qb[e];
+        }
+        int sum = (int)(usum - 8u * 0x4B400000u);
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);                                                       // 4 lanes = one slab
         if (valid) {
-            auto pack = [&](int i0, int i1, int i2, int i3, int sh) -> uint32_t {
-                return ((uint32_t)(q[i0] >> sh) & 0xffu) | (((uint32_t)(q[i1] >> sh) & 0xffu) << 8) |
-                       (((uint32_t)(q[i2] >> sh) & 0xffu) << 16) | (((uint32_t)(q[i3] >> sh) & 0xffu) << 24);
+            // byte planes of (q0, q4, q1, q5) | (q2, q6, q3, q7): high bytes (signed) and low bytes (unsigned)
+            auto pack = [&](int i0, int i1, int i2, int i3, uint32_t sel) -> uint32_t {
+                return __byte_perm(__byte_perm(qb[i0], qb[i1], sel), __byte_perm(qb[i2], qb[i3], sel), 0x5410u);
             };
-            const int si = o >> 2, j = o & 3;
             uint2 hw, lw;
-            hw.x = pack(0, 4, 1, 5, 8); hw.y = pack(2, 6, 3, 7, 8);
-            lw.x = pack(0, 4, 1, 5, 0); lw.y = pack(2, 6, 3, 7, 0);
+            hw.x = pack(0, 4, 1, 5, 0x0051u); hw.y = pack(2, 6, 3, 7, 0x0051u);
+            lw.x = pack(0, 4, 1, 5, 0x0040u); lw.y = pack(2, 6, 3, 7, 0x0040u);
+            const int si = o >> 2, j = o & 3;
             *reinterpret_cast<uint2*>(act_g + (size_t)si * 64 + j * 8) = hw;
             *reinterpret_cast<uint2*>(act_g + (size_t)si * 64 + 32 + j * 8) = lw;
             if (j == 0) asum_s[si] = sum;
@@ -485,15 +499,13 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     // ---- main loop: this warp alone, stage by stage; everything positional comes from the stage list.
     int am[4] = {0, 0, 0, 0}, ae[2] = {0, 0};
     float tot = 0.f;
-    int S = 0, cslot = 0, blk_slabs = 0, emits = 0;
-    uint32_t phase = 0;
+    int S = 0, blk_slabs = 0, emits = 0;
 #pragma unroll 1
     for (int s = 0; s < nst; ++s) {
-        mbar_wait(bar0 + (uint32_t)cslot * 8u, (phase >> cslot) & 1u);
-        phase ^= 1u << cslot;
+        mbar_wait(bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u, ((uint32_t)s >> 3) & 1u);
         const uint4 d = lds128(list + (uint32_t)s * 16u);
         const int ks = (int)(d.z & 0x7ffu), n = (int)((d.z >> 11) & 7u), bits = (int)((d.z >> 14) & 15u);
-        const uint32_t slot = ring + (uint32_t)(cslot * P.slot_bytes);
+        const uint32_t slot = ring + ((d.w >> 16) & 0xffu) * 128u;
         const uint32_t xs = act + (uint32_t)ks * 64u, as = asum + (uint32_t)ks * 4u;
         switch (bits) {
             case 4: S += consume_stage<4>(slot, n, xs, as, lane, am, ae); break;
@@ -504,8 +516,12 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
             default: S += consume_stage<2>(slot, n, xs, as, lane, am, ae); break;
         }
         __syncwarp();
-        if (lane == 0 && s + ns < nst) issue_stage(s + ns, cslot);            // refill the slot just drained
-        cslot = (cslot + 1 == ns) ? 0 : cslot + 1;
+        {                                          // the space this stage occupied is free: request the stages waiting for it
+            const int nreq = (int)((d.w >> 24) & 15u);
+            if (lane == 0)
+                for (int j = 0; j < nreq; ++j) issue_stage(next_req + j);
+            next_req += nreq;
+        }
         blk_slabs += n;
         if (d.z & (DF_FLUSH << 18)) {
             // integer sums -> fp32:  sum_k a_k (q_k - zero) * scale  =  (sum a q - zero * sum a) * scale_w * scale_row
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
             S = 0;
             if (s + 1 < nst) wraw = fetch_scale(lds128(list + (uint32_t)(s + 1) * 16u));      // scales of the next group
             if (d.z & (DF_BLOCK_DONE << 18)) {
-                const int blk = blk0 + (int)d.w;
+                const int blk = blk0 + (int)(d.w & 0xffffu);
                 if (blk_slabs == KS) {
                     finalize_block(P, blk, lane, tot * rrms);          // this warp covered the block's whole K by itself
                 } else {
@@ -555,6 +571,12 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         finalize_block(P, blk, lane, v * rrms);
     }
     if (P.dbg && lane == 0) atomicMax(P.dbg + 7, i8_gtimer());
+    if (P.dbg_rec && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.dbg_rec[blockIdx.x * 4 + 2] = i8_gtimer();
+        P.dbg_rec[blockIdx.x * 4 + 3] = smid;
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------
@@ -626,7 +648,7 @@ struct I8Plan {
     uint4* d_desc = nullptr;
     uint32_t* d_first = nullptr;
     uint32_t* d_cta = nullptr;
-    int ctas = 0, lcap = 0, slot_bytes = 0, max_bits = 0;
+    int ctas = 0, lcap = 0, arena = 0;
 };
 struct I8PlanMat {
     int N, KS, is_gptq, num_regions;
@@ -637,7 +659,7 @@ static std::map<std::string, I8Plan> g_plans[64];
 static std::mutex g_plan_mutex;
 
 // stage lists of one launch structure: the same walk for every (CTA, warp) -- units are (block, slab) pairs, CTA-relative
-static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* cta_blk, int C, int warps, int slot_bytes,
+static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* cta_blk, int C, int warps, int arena,
                            std::vector<uint4>& desc, std::vector<uint32_t>& first, std::vector<uint32_t>& cta, int* lcap) {
     const int KS = mats[0].KS;
     int blk_base[I8_MAX_MATS + 1] = {0};
@@ -664,7 +686,7 @@ static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* 
                 const int gend = rg.ks_begin + ((g + 1) << rg.spg_log2);
                 // a stage never crosses a quantisation group, a 128-k row block, a bit-width region or the end of the warp's range
                 const int segend = std::min(std::min(gend, (ks | 3) + 1), std::min(r_end, ks + (l1 - lin)));
-                const int len = segend - ks, cap = std::max(1, std::min(4, slot_bytes / (128 * rg.bits)));
+                const int len = segend - ks, cap = std::max(1, std::min(4, (arena / 2) / (128 * rg.bits)));
                 const int pieces = (len + cap - 1) / cap, n = (len + pieces - 1) / pieces;
                 uint32_t flags = (ks + n == segend ? DF_FLUSH : 0u) | ((ks + n == KS || lin + n == l1) ? DF_BLOCK_DONE : 0u) | (m.is_gptq ? DF_GPTQ : 0u);
                 if (flags & DF_BLOCK_DONE) flags |= DF_FLUSH;
@@ -677,7 +699,40 @@ static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* 
                 desc.push_back(d);
                 lin += n;
             }
-            *lcap = std::max(*lcap, (int)(desc.size() - first.back()));
+            // place the warp's stages in its byte arena (a ring): `req` of stage c = how many later stages may be requested once c
+            // has been consumed; n_pre = how many are requested up front.  At most I8_BARS stages are ever in flight.
+            const size_t w0 = first.back(), nst = desc.size() - w0;
+            *lcap = std::max(*lcap, (int)nst);
+            std::vector<int> dep(nst, -1);
+            {
+                struct Live { int idx; uint32_t off, size; };
+                std::vector<Live> live;
+                uint32_t off = 0;
+                int last_dep = -1;
+                for (size_t s = 0; s < nst; ++s) {
+                    const uint4& d = desc[w0 + s];
+                    const uint32_t size = ((d.z >> 11) & 7u) * ((d.z >> 14) & 15u) * 128u;
+                    if (off + size > (uint32_t)arena) off = 0;
+                    auto overlaps = [&](const Live& l) { return l.off < off + size && off < l.off + l.size; };
+                    for (;;) {
+                        bool hit = false;
+                        for (const Live& l : live) hit = hit || overlaps(l);
+                        if (!hit && (int)live.size() < I8_BARS) break;
+                        last_dep = live.front().idx;          // consumption is in order: free the oldest
+                        live.erase(live.begin());
+                    }
+                    dep[s] = last_dep;
+                    live.push_back(Live{(int)s, off, size});
+                    desc[w0 + s].w |= (off / 128u) << 16;
+                    off += size;
+                }
+            }
+            int n_pre = 0;
+            for (size_t s = 0; s < nst; ++s) {
+                if (dep[s] < 0) ++n_pre;
+                else desc[w0 + dep[s]].w += 1u << 24;
+            }
+            first.back() |= (uint32_t)n_pre << 26;
         }
     }
     first.push_back((uint32_t)desc.size());
@@ -696,18 +751,24 @@ static int i8_get_plan(int device, const I8PlanMat* mats, int nm, int sms, int w
     for (int i = 0; i < nm; ++i) {
         // only blocks that hold real columns (the last strip of a padded matrix may contain all-padding blocks)
         for (int b = 0; b < (mats[i].N + 31) / 32; ++b) blk_bytes.push_back(mats[i].blk_stream_bytes);
-        for (int r = 0; r < mats[i].num_regions; ++r) pl.max_bits = std::max(pl.max_bits, mats[i].reg[r].bits);
     }
     EXL2B_REQUIRE(blk_bytes.size() < 65535, "too many column blocks (%zu)", blk_bytes.size());
     EXL2B_REQUIRE((long long)blk_bytes.size() * mats[0].KS < (1ll << 30), "problem too large for 32-bit unit arithmetic");
     unsigned short cta_blk[I8_MAX_CTAS + 1];
     i8_partition_blocks(blk_bytes, sms, cta_blk, &pl.ctas);
-    // ring slot: 2 KB holds 4 slabs up to 4 bits; wider planes get 3 KB slots (4 slabs at 5 / 6 bits, 3 at 8)
-    static const int slot_override = [] { const char* e = getenv("EXL2B_I8_SLOT"); return e ? atoi(e) : 0; }();
-    pl.slot_bytes = slot_override ? slot_override : (pl.max_bits > 4 ? 3072 : 2048);
+    // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: a CTA gets at most
+    // 112 KB (EXL2B_I8_SMEM overrides), and what the staged row / lists leave of it is split into the warps' weight arenas
+    static const int smem_budget = [] { const char* e = getenv("EXL2B_I8_SMEM"); return e ? atoi(e) : 112 * 1024; }();
     std::vector<uint4> desc;
     std::vector<uint32_t> first, cta;
-    i8_build_lists(mats, nm, cta_blk, pl.ctas, warps, pl.slot_bytes, desc, first, cta, &pl.lcap);
+    pl.arena = 8192;
+    for (;;) {
+        desc.clear(); first.clear(); cta.clear();
+        i8_build_lists(mats, nm, cta_blk, pl.ctas, warps, pl.arena, desc, first, cta, &pl.lcap);
+        if ((int)i8_smem_map(warps, pl.arena, mats[0].KS, pl.lcap).total <= smem_budget || pl.arena <= 2048) break;
+        pl.arena -= 256;
+    }
+    EXL2B_REQUIRE(desc.size() < (1u << 26), "too many stages");
     EXL2B_CUDA(cudaMalloc(&pl.d_desc, desc.size() * sizeof(uint4) + 16));
     EXL2B_CUDA(cudaMalloc(&pl.d_first, first.size() * 4));
     EXL2B_CUDA(cudaMalloc(&pl.d_cta, cta.size() * 4));
@@ -790,21 +851,15 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.plan_first = pl.d_first;
     P.plan_cta = pl.d_cta;
     P.lcap = pl.lcap;
-    P.slot_bytes = pl.slot_bytes;
-
-    auto smem_for = [&](int ns) { return (size_t)i8_smem_map(warps, ns, P.slot_bytes, P.KS, P.lcap).total; };
-    // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: the deepest ring
-    // (<= 4 slots per warp) that keeps the CTA <= 112 KB, never fewer than 2 slots
-    P.ns = I8_MAX_STAGES;
-    while (P.ns > 2 && smem_for(P.ns) > 112 * 1024) --P.ns;
-    static const int ns_override = [] { const char* e = getenv("EXL2B_I8_NS"); return e ? atoi(e) : 0; }();     // tuning knob
-    if (ns_override >= 2 && ns_override <= I8_MAX_STAGES) P.ns = ns_override;
-    const size_t smem_total = smem_for(P.ns);
+    P.arena = pl.arena;
+    const size_t smem_total = i8_smem_map(warps, P.arena, P.KS, P.lcap).total;
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes, K = %d)", smem_total, P.K);
     extern unsigned long long* g_dbg;
     extern int g_dbg_cta, g_dbg_slot;
     P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
+    extern unsigned long long* g_dbg_rec;
+    P.dbg_rec = (g_dbg_rec && P.dbg) ? g_dbg_rec + (size_t)((g_dbg_slot - 1) % 64) * I8_MAX_CTAS * 4 : nullptr;
     const int C = pl.ctas;
     if (warps == 16) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
     else if (warps == 12) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
@@ -839,7 +894,7 @@ extern "C" int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_
     exl2b::i8_partition_blocks(bb, ctas, cta_blk, ctas_used);
     std::vector<uint4> d;
     std::vector<uint32_t> f, c;
-    exl2b::i8_build_lists(&m, 1, cta_blk, *ctas_used, warps, slot_bytes, d, f, c, lcap);
+    exl2b::i8_build_lists(&m, 1, cta_blk, *ctas_used, warps, slot_bytes, d, f, c, lcap);      // slot_bytes = bytes of a warp's arena
     EXL2B_REQUIRE((int)d.size() <= cap_desc, "descriptor buffer too small (%zu)", d.size());
     memcpy(desc, d.data(), d.size() * sizeof(uint4));
     memcpy(first, f.data(), f.size() * 4);

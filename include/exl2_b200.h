@@ -168,6 +168,8 @@ int exl2b_debug_set(int ctas_per_sm, unsigned long long* stamps, int cta);
 /* Host-only diagnostics (no GPU needed): the 32-column-block -> CTA partition the batch-1 GEMV uses for blocks of the given
  * byte sizes; out[0..*used] are the block boundaries of the CTAs. */
 int exl2b_debug_partition(const uint32_t* block_bytes, int num_blocks, int ctas, uint16_t* out, int* used);
+/* diagnostics: per-CTA records (start, wait over, end, SM id) of the batch-1 GEMV launches, [64][160][4] uint64, or NULL */
+int exl2b_debug_set_records(unsigned long long* records);
 /* host-only: the per-warp stage lists of the batch-1 GEMV for one matrix structure (tests/test_i8_emulation.py) */
 int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_bytes, const int* regions, int num_regions, int ctas, int warps,
                      int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap);

@@ -230,7 +230,7 @@ def test_block_partition(name, bb, ctas):
 # flag closes every group / row block / range, the block-done flag the warp's share of a block.
 
 
-def _plan(N, KS, regions, ctas=148, warps=16, slot=3072, gptq=0):
+def _plan(N, KS, regions, ctas=148, warps=16, slot=6144, gptq=0):
     import ctypes
 
     from exllamav2_b200 import ext as ext_c
@@ -269,11 +269,13 @@ PLAN_CASES = [
 
 
 @pytest.mark.parametrize("name,N,KS,regions", PLAN_CASES, ids=[c[0] for c in PLAN_CASES])
-@pytest.mark.parametrize("warps,slot", [(16, 3072), (12, 2048)])
+@pytest.mark.parametrize("warps,slot", [(16, 6144), (12, 4096), (16, 2048)])
 def test_stage_lists(name, N, KS, regions, warps, slot):
     desc, first, C, lcap, stream_bytes, reg = _plan(N, KS, regions, warps=warps, slot=slot)
     nblk = (N + 31) // 32
     seen = np.zeros((nblk, KS), dtype=np.int32)
+    n_pre_all = (first >> 26).astype(int)
+    first = first & 0x3FFFFFF
     assert first[0] == 0 and first[-1] == len(desc) and np.all(np.diff(first.astype(np.int64)) >= 0)
     assert lcap == int(np.max(np.diff(first.astype(np.int64))))
     # CTA block ranges: recover from the partition hook (same inputs)
@@ -283,11 +285,33 @@ def test_stage_lists(name, N, KS, regions, warps, slot):
     for c in range(C):
         for w in range(warps):
             lst = desc[first[c * warps + w]: first[c * warps + w + 1]]
+            # the arena (`slot` bytes per warp) as the kernel drives it: stages are requested up front / as space frees, never over
+            # a stage that has not been consumed, at most 8 in flight (one mbarrier each), and always before they are waited for
+            requested, live = n_pre_all[c * warps + w], {}
+            sizes = [int(((z >> 11) & 7) * ((z >> 14) & 15) * 128) for (_, _, z, _) in lst]
+            offs = [int((bw >> 16) & 0xFF) * 128 for (_, _, _, bw) in lst]
+
+            def request(sidx):
+                assert offs[sidx] + sizes[sidx] <= slot
+                for j, (o, sz) in live.items():
+                    assert offs[sidx] + sizes[sidx] <= o or o + sz <= offs[sidx], "arena overlap with an unconsumed stage"
+                    assert j % 8 != sidx % 8, "mbarrier still in use"
+                live[sidx] = (offs[sidx], sizes[sidx])
+            for sidx in range(min(requested, len(lst))):
+                request(sidx)
+            assert requested <= len(lst) and (requested >= 1 or len(lst) == 0)
+            for cidx in range(len(lst)):
+                assert cidx < requested, "stage waited for before it was requested"
+                del live[cidx]
+                for _ in range(int((lst[cidx][3] >> 24) & 15)):
+                    request(requested)
+                    requested += 1
+            assert requested == len(lst)
             prev = None
             for i, (x, y, z, bw) in enumerate(lst):
                 ks, n, bits, flags, mi = z & 0x7FF, (z >> 11) & 7, (z >> 14) & 15, (z >> 18) & 15, (z >> 22) & 3
-                blk = bounds[c] + int(bw)
-                assert mi == 0 and 1 <= n <= 4 and n * bits * 128 <= slot
+                blk = bounds[c] + int(bw & 0xFFFF)
+                assert mi == 0 and 1 <= n <= 4 and (n == 1 or n * bits * 128 <= slot // 2)
                 r = max(j for j, rg in enumerate(regions) if ks >= rg[0])
                 ks0, rb, lg = regions[r]
                 assert bits == rb and ks + n <= ends[ks0], "one region"

@@ -1,9 +1,9 @@
 #!/bin/bash
-# GPU box helper: warp-count / ring-depth sweep of the batch-1 GEMV (microbench, graph replay).  usage: tools/gpu_sweep.sh <tag>
+# GPU box helper: warp-count / shared-memory-budget sweep of the batch-1 GEMV (microbench, graph replay).  usage: tools/gpu_sweep.sh <tag>
 TAG=${1:-sweep}
-for W in 16 12 8; do for NS in 0 2; do
-  echo "== warps $W ns $NS"
-  EXL2B_I8_WARPS=$W EXL2B_I8_NS=$NS timeout 200 python tools/microbench.py --shapes qkvo54,gateup54,down43,head --m 1 2>&1 | python -c '
+for W in 16 12; do for SM in 114688 98304; do
+  echo "== warps $W smem $SM"
+  EXL2B_I8_WARPS=$W EXL2B_I8_SMEM=$SM timeout 200 python tools/microbench.py --shapes qkvo54,gateup54,down43,head --m 1 2>&1 | python -c '
 import sys, json
 for l in sys.stdin:
     try: d = json.loads(l)
