@@ -54,6 +54,9 @@ struct AttnQ4Params {
     // and leaves (max, sum, unnormalised rotated output) in `ws`; the last to arrive (counter) merges.  Chunks are at least
     // AQ_SPLIT_MIN positions, so short contexts use one CTA and never touch the workspace.
     int sc_len;             // floats of the score buffer
+    int batch;              // grid: one CTA per (head, sequence, split), flattened on x, padded to one CTA per SM with slot holders
+    int busy_ctas;          //   = H * batch * nsplit
+    unsigned int* slot_cnt; // CTAs of this launch that are done (self-resetting), see gemv_i8.cu
     int nsplit;
     float* ws;              // [batch][H][nsplit][hd + 2]
     unsigned int* cnt;      // [batch][H]
@@ -65,9 +68,11 @@ __device__ __forceinline__ unsigned long long aq_gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define AQ_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) P.dbg[i] = aq_gtimer(); \
+#define AQ_STAMP(i) do { if (P.dbg) { if (blockIdx.x == P.dbg_cta && threadIdx.x == 0) P.dbg[i] = aq_gtimer(); \
                                       if ((i) == 0 && threadIdx.x == 0) atomicMin(P.dbg + 6, aq_gtimer()); } } while (0)
 constexpr int AQ_SPLIT_MIN = 512;
+// every exit of a working CTA: count it (slot holders of the launch leave when all working CTAs have)
+#define AQ_EXIT do { if (threadIdx.x == 0 && atomicAdd(P.slot_cnt, 1u) == gridDim.x - 1u) *reinterpret_cast<volatile unsigned int*>(P.slot_cnt) = 0u; return; } while (0)
 constexpr int AQ_STAGE = 512;          // cached positions per CTA staged in shared memory before the dependency wait
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -135,6 +140,17 @@ __device__ __forceinline__ half2 hadamard32_h(half2 w2, int lane) {      // bit-
     return w2;
 }
 
+__device__ __forceinline__ int aq_dp4a_us(uint32_t a, uint32_t b, int c) {      // a: 4 unsigned bytes, b: 4 signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int aq_dp4a_uu(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // (nibble - 8) as fp32 without I2F: 0x4B000000 | n is the float 2^23 + n
 __device__ __forceinline__ float nib_f(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388616.0f; }
 
@@ -145,14 +161,18 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     constexpr int VEC = HD / 32;            // values per lane in the dims-on-lanes phase
     constexpr int UNITS = HD / 64;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z;
+    const int h = (int)blockIdx.x % P.H, b = ((int)blockIdx.x / P.H) % P.batch, z = (int)blockIdx.x / (P.H * P.batch);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = P.H / P.KVH, kvh = h / group;
     __shared__ int s_last;
 
     constexpr int QPAD = 36;               // floats per 32-value block of the rotated query (bank-staggered: 4 blocks, 4 threads per row)
+    constexpr int QIB = 80;                // bytes per 32-value block of the integer query operands (64 used; bank-staggered like QPAD)
     float* qrot = reinterpret_cast<float*>(smem);                          // [NSC][QPAD]
-    float* red = qrot + NSC * QPAD;                                                // [AQ_WARPS][HD]
+    uint8_t* qi = reinterpret_cast<uint8_t*>(qrot + NSC * QPAD);           // [NSC][QIB]  16-bit query as dp4a byte operands (below)
+    int* qsum = reinterpret_cast<int*>(qi + NSC * QIB);                    // [NSC]  sum of a block's 16-bit values
+    float* qscl = reinterpret_cast<float*>(qsum + NSC);                    // [NSC]  its power-of-two scale
+    float* red = qscl + NSC;                                               // [AQ_WARPS][HD]
     float* wred = red + AQ_WARPS * HD;                                     // [2 * AQ_WARPS]
     uint8_t* new_q = reinterpret_cast<uint8_t*>(wred + 2 * AQ_WARPS);      // [2][AQ_MAX_QLEN][ROWB]
     half* new_s = reinterpret_cast<half*>(new_q + 2 * AQ_MAX_QLEN * ROWB); // [2][AQ_MAX_QLEN][NSC]
@@ -166,6 +186,13 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
 
     AQ_STAMP(0);
     griddep_launch_dependents();
+    if ((int)blockIdx.x >= P.busy_ctas) {          // slot holder (gemv_i8.cu): keeps this SM's slot until the working CTAs are done
+        if (threadIdx.x == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(P.slot_cnt) < (unsigned)P.busy_ctas) __nanosleep(200);
+            if (atomicAdd(P.slot_cnt, 1u) == gridDim.x - 1u) *reinterpret_cast<volatile unsigned int*>(P.slot_cnt) = 0u;
+        }
+        return;
+    }
     // ---- 0. before the dependency wait: everything that only touches state written by EARLIER steps / layers -- the
     //      sequence length, the page table and the cached rows (this layer's cache was last written one decode step ago; the
     //      kernel in front of us in the stream, the Q|K|V projection, writes none of it).  The first cached K row of every
@@ -173,7 +200,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     const int seqlen = P.cache_seqlens[b];
     if (seqlen < 0 || seqlen + P.q_len > P.max_ctx) {      // the page table / score buffer end here: refuse instead of corrupting
         if (tid == 0 && P.err) atomicOr(P.err, 1);
-        return;
+        AQ_EXIT;
     }
     const int32_t* btg = P.block_table + (size_t)b * P.pages_per_seq;
     // this CTA's share of the positions (the whole context unless split-KV is active and the context is long)
@@ -181,7 +208,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     if (P.nsplit > 1) {
         const int n_all = seqlen + 1;
         ns_act = min(P.nsplit, max(1, (n_all + AQ_SPLIT_MIN - 1) / AQ_SPLIT_MIN));
-        if (z >= ns_act) return;
+        if (z >= ns_act) AQ_EXIT;
         const int chunk = (n_all + ns_act - 1) / ns_act;
         p_lo = z * chunk;
         p_hi = min(n_all, p_lo + chunk);
@@ -223,8 +250,33 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         float2 w = hadamard32_f(__half22float2(qh), lane);
         const float f = P.scale_log2 * (1.0f / 32.0f);
         const int e = un * 64 + 2 * lane;
-        qrot[(e >> 5) * QPAD + (e & 31)] = w.x * f;
-        qrot[(e >> 5) * QPAD + (e & 31) + 1] = w.y * f;
+        w.x *= f;
+        w.y *= f;
+        qrot[(e >> 5) * QPAD + (e & 31)] = w.x;
+        qrot[(e >> 5) * QPAD + (e & 31) + 1] = w.y;
+        // The cached rows are scored on the integer dot-product instruction (like the batch-1 GEMV): the block's 32 values as 16-bit
+        // integers with a power-of-two scale (error <= 2^-15 of the block maximum), split into a signed high and an unsigned low
+        // byte plane, bytes ordered as the masked nibble words of a cached row present them: word j of a block holds values 8j..8j+7,
+        // (x & 0x0f0f0f0f) = values 8j + {0,2,4,6}, (x & 0xf0f0f0f0) = 16 * values 8j + {1,3,5,7}.
+        float amax = fmaxf(fabsf(w.x), fabsf(w.y));
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));      // 16 lanes = one block
+        const uint32_t ef = (__float_as_uint(amax * 1.000030518f) >> 23) & 0xffu;
+        const float inv = amax > 0.f ? __uint_as_float((268u - ef) << 23) : 0.f;
+        const uint32_t q0 = __float_as_uint(fmaf(w.x, inv, 12582912.f)), q1 = __float_as_uint(fmaf(w.y, inv, 12582912.f));
+        int sum = (int)(q0 + q1 - 2u * 0x4B400000u);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const int blk = e >> 5, l16 = lane & 15, j = l16 >> 2, m = l16 & 3;
+        uint8_t* qb = qi + blk * QIB + j * 16 + m;          // word order per j: even-high, even-low, odd-high, odd-low
+        qb[0] = (uint8_t)(q0 >> 8);
+        qb[4] = (uint8_t)q0;
+        qb[8] = (uint8_t)(q1 >> 8);
+        qb[12] = (uint8_t)q1;
+        if (l16 == 0) {
+            qsum[blk] = sum;
+            qscl[blk] = amax > 0.f ? __uint_as_float((ef - 14u) << 23) : 0.f;
+        }
     };
     if (warp >= AQ_WARPS - UNITS) rotate_q(0, warp - (AQ_WARPS - UNITS));
     const int n_jobs = 2 * P.q_len * UNITS;
@@ -276,26 +328,25 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         }
     }
 
-    // score of one 32-value block of a cached row (4-bit values, one fp16 scale) against its block of the rotated query
+    AQ_STAMP(8);
+
+    // score of one 32-value block of a cached row (4-bit values, one fp16 scale) against its block of the rotated query:
+    // sum_d (nib_d - 8) q_d = sum nib q - 8 sum q, all in integers (dp4a on the masked words), one fp32 multiply at the end
     auto score_blk = [&](uint4 kq, uint32_t ks) {
-        const float* qb_ = qrot + kblk * QPAD;
+        const uint8_t* qb = qi + kblk * QIB;
         const uint32_t ww[4] = {kq.x, kq.y, kq.z, kq.w};
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4 qa = *reinterpret_cast<const float4*>(qb_ + j * 8);
-            const float4 qb = *reinterpret_cast<const float4*>(qb_ + j * 8 + 4);
-            const uint32_t x = ww[j];
-            a0 = fmaf(nib_f(x & 15u), qa.x, a0);
-            a1 = fmaf(nib_f((x >> 4) & 15u), qa.y, a1);
-            a2 = fmaf(nib_f((x >> 8) & 15u), qa.z, a2);
-            a3 = fmaf(nib_f((x >> 12) & 15u), qa.w, a3);
-            a0 = fmaf(nib_f((x >> 16) & 15u), qb.x, a0);
-            a1 = fmaf(nib_f((x >> 20) & 15u), qb.y, a1);
-            a2 = fmaf(nib_f((x >> 24) & 15u), qb.z, a2);
-            a3 = fmaf(nib_f(x >> 28), qb.w, a3);
+            const uint4 qo = *reinterpret_cast<const uint4*>(qb + j * 16);
+            const uint32_t lo = ww[j] & 0x0f0f0f0fu, hi = ww[j] & 0xf0f0f0f0u;
+            a0 = aq_dp4a_us(lo, qo.x, a0);          // unsigned nibbles x signed high bytes
+            a1 = aq_dp4a_uu(lo, qo.y, a1);          // unsigned x unsigned low bytes
+            a2 = aq_dp4a_us(hi, qo.z, a2);
+            a3 = aq_dp4a_uu(hi, qo.w, a3);
         }
-        return __half2float(__ushort_as_half((unsigned short)ks)) * ((a0 + a1) + (a2 + a3));
+        const int v = ((a0 << 8) + a1) + (((a2 << 8) + a3) >> 4) - 8 * qsum[kblk];
+        return __half2float(__ushort_as_half((unsigned short)ks)) * qscl[kblk] * (float)v;
     };
 
     for (int i = 0; i < P.q_len; ++i) {
@@ -371,6 +422,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
                     if (pb + u * RPP < n_ctx) score_pos(pb + u * RPP + krow, kq[u], ks[u]);
             }
         }
+        AQ_STAMP(9);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         if (lane == 0) wred[warp] = lmax;
@@ -477,7 +529,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
                 __threadfence();
             }
             __syncthreads();
-            if (!s_last) return;
+            if (!s_last) AQ_EXIT;
             if (warp < UNITS) {
                 const float* base = P.ws + ((size_t)b * P.H + h) * P.nsplit * (HD + 2);
                 float M = -INFINITY;
@@ -508,7 +560,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
                     }
                 }
             }
-            return;
+            AQ_EXIT;
         }
         if (warp < UNITS) {
             float2 w = make_float2(0.f, 0.f);
@@ -536,6 +588,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         __syncthreads();
     }
     if (P.dbg && threadIdx.x == 0) atomicMax(P.dbg + 7, aq_gtimer());
+    AQ_EXIT;
 }
 
 }  // namespace exl2b
@@ -651,7 +704,7 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
     const int sc_len = nsplit > 1 ? std::max(AQ_SPLIT_MIN, (P.max_ctx + nsplit) / nsplit) + 8 : P.max_ctx + q_len;
     const int hd = head_dim;
     P.sc_len = sc_len;
-    const size_t smem = (size_t)((hd / 32) * 36 + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
+    const size_t smem = (size_t)((hd / 32) * 36 + AQ_WARPS * hd + 2 * AQ_WARPS) * 4 + (size_t)(hd / 32) * (80 + 8) + 2 * AQ_MAX_QLEN * (hd / 2) + 2 * AQ_MAX_QLEN * (hd / 32) * 2 +
                         (size_t)2 * AQ_MAX_QLEN * hd * 4 + (size_t)((pages_per_seq + 3) & ~3) * 4 + (size_t)((sc_len + 3) & ~3) * 4 +
                         (size_t)AQ_STAGE * (hd / 2) * 2 + (size_t)AQ_STAGE * (hd / 32) * 2 * 2;
     EXL2B_REQUIRE(smem <= 200 * 1024, "context of %d tokens does not fit the score buffer", P.max_ctx);
@@ -661,7 +714,16 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
         EXL2B_CUDA(cudaFuncSetAttribute(attn_q4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[dev] = true;
     }
-    dim3 grid(num_heads, batch, nsplit);
+    static unsigned int* slot_cnts[64] = {nullptr};
+    static std::atomic<unsigned> launch_seq{0};
+    if (!slot_cnts[dev]) {
+        EXL2B_CUDA(cudaMalloc(&slot_cnts[dev], 128 * sizeof(unsigned int)));
+        EXL2B_CUDA(cudaMemset(slot_cnts[dev], 0, 128 * sizeof(unsigned int)));
+    }
+    P.slot_cnt = slot_cnts[dev] + (launch_seq.fetch_add(1) % 127u);
+    P.batch = batch;
+    P.busy_ctas = num_heads * batch * nsplit;
+    dim3 grid(std::max(P.busy_ctas, device_sm_count(dev)));
     if (head_dim == 128)
         EXL2B_CUDA(launch_pdl(attn_q4_kernel<128>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
     else

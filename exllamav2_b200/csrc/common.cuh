@@ -94,6 +94,11 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
                  : "memory");
 }
 
+// bulk prefetch of a global range into L2 (no shared memory, no completion to wait for).  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

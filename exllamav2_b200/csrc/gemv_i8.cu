@@ -53,7 +53,7 @@ struct I8Mat {
 // quantisation group and one 128-k row block.  16 bytes, built ON THE HOST once per launch structure (I8Plan below):
 //   x = byte offset of the stage inside its matrix' packed buffer
 //   y = element index of lane 0's entry in the matrix' scale table (group * N + first column of the block)
-//   z = ks | slabs << 11 | bits << 14 | flags << 18 | matrix << 22
+//   z = ks | slabs << 11 | bits << 14 | flags << 18 | matrix << 22 | (bytes / 128) << 24
 //   w = block index relative to the CTA's first block | (byte offset of the stage in the warp's arena / 128) << 16
 //       | (stages to request once this one is consumed) << 24
 // A warp's weight arena is a byte ring (not fixed slots): the host places every stage, records after which stage's consumption its
@@ -67,6 +67,7 @@ struct I8Params {
     const uint4* plan_desc;           // stage descriptors, warp after warp, CTA after CTA
     const uint32_t* plan_first;       // [ctas * warps + 1] first descriptor of every warp | stages to request up front << 26
     const uint32_t* plan_cta;         // [ctas] first block | blocks << 16
+    const uint32_t* plan_red;         // [blocks] bit w: warp w holds a partial sum of the block | the first such warp's partial slot << 16
     int num_mats, K, KS;
     const uint16_t* perm;             // stored row k' <- feature perm[k'], or NULL
     const half* x;
@@ -74,8 +75,11 @@ struct I8Params {
     const half* norm_w;
     float norm_eps;
     int mode, x_permuted;
+    int norm_permuted;                // norm_w is already in stored-row order (QMatrix::normp_buf)
+    int l2_prefetch;                  // prefetch the part of a warp's share that does not fit its arena into L2 before the wait
     int arena;                        // bytes of a warp's weight arena
-    int lcap;                         // most stages any warp has
+    int busy_ctas;                    // CTAs that own blocks; the rest of the grid only keeps its SM slot occupied (see the kernel)
+    unsigned int* slot_cnt;           // CTAs of this launch that are done (self-resetting)
     unsigned long long* dbg;          // optional globaltimer stamps (exl2b_debug_set), NULL in production
     int dbg_cta;
     unsigned long long* dbg_rec;      // optional per-CTA records [cta][4]: start, dependency wait over, end, SM id
@@ -83,17 +87,16 @@ struct I8Params {
 
 // dynamic shared-memory map of a CTA (byte offsets, every region 16-byte aligned) -- one definition for host and device
 struct I8Smem {
-    uint32_t act, asum, ascale, emit, list, total;
+    uint32_t act, asum, ascale, emit, total;
 };
-__host__ __device__ inline I8Smem i8_smem_map(int warps, int arena, int KS, int lcap) {
+__host__ __device__ inline I8Smem i8_smem_map(int warps, int arena, int KS) {
     auto up = [](uint32_t x) { return (x + 15u) & ~15u; };
     I8Smem m;
     m.act = up((uint32_t)warps * (uint32_t)arena);                   // staged row: [KS][64 B]
     m.asum = up(m.act + (uint32_t)KS * 64u);                          // [KS] integer sum of a slab's row values
     m.ascale = up(m.asum + (uint32_t)KS * 4u);                        // [KS/4 + 1] scale of a 128-k block
     m.emit = up(m.ascale + (uint32_t)(KS / 4 + 1) * 4u);              // [warp][2][32] partial sums of split blocks
-    m.list = up(m.emit + (uint32_t)warps * 256u);                     // [warp][lcap] stage descriptors
-    m.total = up(m.list + (uint32_t)warps * (uint32_t)lcap * 16u);
+    m.total = up(m.emit + (uint32_t)warps * 256u);
     return m;
 }
 
@@ -111,8 +114,9 @@ __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
 
 // ---- one slab (32 k) of the warp's 32-column block: integer dot products, one column per lane -------------------------------
 // Staged row of a slab (64 B): XH[2j] / XH[2j+1] = high bytes of k = 8j + {0,4,1,5} / 8j + {2,6,3,7}; XL the low bytes.
-// That is the byte order (w & 0x0f0f0f0f) / (w & 0xf0f0f0f0) of a 4-bit plane word has (layout.h: field e of pair slot j
-// at bit 16e + 4j, k = 8w + 2j + e); other planes reach their order with one PRMT per operand.
+// That is the byte order every plane's masked words have (layout.h pair_word / pair_slot): (w & 0x0f0f0f0f) / (w & 0xf0f0f0f0)
+// of 4-bit word j meet XH[2j] / XH[2j+1]; field position i of 2-bit word w meets XH[4w + i]; bit position i of the 1-bit word
+// meets XH[i]; 8-bit word w meets XH[w].  No operand is ever permuted.
 template <int BITS>
 __device__ __forceinline__ void consume_slab(uint32_t wb, uint32_t xs, int lane, int (&am)[4], int (&ae)[2]) {
     constexpr int Pm = plane_main(BITS), Pe = plane_extra(BITS);
@@ -154,40 +158,33 @@ __device__ __forceinline__ void consume_slab(uint32_t wb, uint32_t xs, int lane,
             am[3] = dp4a_uu(hi, XL[2 * j + 1], am[3]);
         }
     } else if constexpr (Pm == 8) {
-        // word w: bytes = k 4w + {0,2,1,3}
         const uint4 a4 = lds128(wb + lane * 16), b4 = lds128(wb + 512 + lane * 16);
         const uint32_t W[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-            const int j = w >> 1;
-            const uint32_t sel = (w & 1) ? 0x7351u : 0x6240u;
-            am[0] = dp4a_us(W[w], __byte_perm(XH[2 * j], XH[2 * j + 1], sel), am[0]);
-            am[1] = dp4a_uu(W[w], __byte_perm(XL[2 * j], XL[2 * j + 1], sel), am[1]);
+            am[0] = dp4a_us(W[w], XH[w], am[0]);
+            am[1] = dp4a_uu(W[w], XL[w], am[1]);
         }
-    } else {   // Pm == 2: word w covers k = 16w .. 16w+15; field i of a byte: k 16w + {2i, 8+2i, 2i+1, 9+2i}
+    } else {   // Pm == 2: field position i of word w meets operand word 4w + i
         const uint2 w2 = lds64(wb + lane * 8);
         const uint32_t W[2] = {w2.x, w2.y};
 #pragma unroll
         for (int w = 0; w < 2; ++w)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int a = 2 * w, b = 2 * w + 1, hi = i & 1;
-                const uint32_t sel = (i & 2) ? 0x7351u : 0x6240u;
                 const uint32_t t = (W[w] >> (2 * i)) & 0x03030303u;
-                am[0] = dp4a_us(t, __byte_perm(XH[2 * a + hi], XH[2 * b + hi], sel), am[0]);
-                am[1] = dp4a_uu(t, __byte_perm(XL[2 * a + hi], XL[2 * b + hi], sel), am[1]);
+                am[0] = dp4a_us(t, XH[4 * w + i], am[0]);
+                am[1] = dp4a_uu(t, XL[4 * w + i], am[1]);
             }
     }
     // ---- extra plane (bits above the main plane), at byte 128 * Pm of the block
-    if constexpr (Pe == 1) {   // one word: bit i of a byte: k = {2i, 16+2i, 2i+1, 17+2i}
+    if constexpr (Pe == 1) {   // one word: bit position i meets operand word i
         const uint32_t w = lds32(wb + 128 * Pm + lane * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int oa = i >> 2, ob = 2 + (i >> 2), t4 = i & 3, hi = t4 & 1;
-            const uint32_t sel = (t4 & 2) ? 0x7351u : 0x6240u;
             const uint32_t t = (w >> i) & 0x01010101u;
-            ae[0] = dp4a_us(t, __byte_perm(XH[2 * oa + hi], XH[2 * ob + hi], sel), ae[0]);
-            ae[1] = dp4a_uu(t, __byte_perm(XL[2 * oa + hi], XL[2 * ob + hi], sel), ae[1]);
+            ae[0] = dp4a_us(t, XH[i], ae[0]);
+            ae[1] = dp4a_uu(t, XL[i], ae[1]);
         }
     } else if constexpr (Pe == 2) {
         const uint2 w2 = lds64(wb + 128 * Pm + lane * 8);
@@ -196,11 +193,9 @@ __device__ __forceinline__ void consume_slab(uint32_t wb, uint32_t xs, int lane,
         for (int w = 0; w < 2; ++w)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int a = 2 * w, b = 2 * w + 1, hi = i & 1;
-                const uint32_t sel = (i & 2) ? 0x7351u : 0x6240u;
                 const uint32_t t = (W[w] >> (2 * i)) & 0x03030303u;
-                ae[0] = dp4a_us(t, __byte_perm(XH[2 * a + hi], XH[2 * b + hi], sel), ae[0]);
-                ae[1] = dp4a_uu(t, __byte_perm(XL[2 * a + hi], XL[2 * b + hi], sel), ae[1]);
+                ae[0] = dp4a_us(t, XH[4 * w + i], ae[0]);
+                ae[1] = dp4a_uu(t, XL[4 * w + i], ae[1]);
             }
     }
 }
@@ -217,19 +212,40 @@ __device__ __forceinline__ int consume_stage(uint32_t slot, int n, uint32_t xs, 
     return S;
 }
 
-__device__ __forceinline__ void finalize_block(const I8Params& P, int blk, int lane, float v) {
+// One lane's output of block `blk`: what is added to it / where its copy in the consumer's row order goes is LOADED by out_pre
+// (raw bits: nothing there waits for memory; the launch's tail calls it before the main loop and touches the values after it),
+// the addresses are recomputed by finalize_block.
+struct I8OutPre {
+    uint32_t add;         // fp16 bits of bias[n] | fp16 bits of the old c[n] << 16   (0 where absent)
+    uint32_t kp;          // index in the consumer's stored-row order (c_perm)
+};
+__device__ __forceinline__ int mat_of_block(const I8Params& P, int blk) {
     int mi = 0;
 #pragma unroll
     for (int i = 1; i < I8_MAX_MATS; ++i)
         if (i < P.num_mats && blk >= P.mat[i].blk_base) mi = i;
-    const I8Mat& m = P.mat[mi];
+    return mi;
+}
+__device__ __forceinline__ I8OutPre out_pre(const I8Params& P, int blk, int lane) {
+    const I8Mat& m = P.mat[mat_of_block(P, blk)];
+    const int n = (blk - m.blk_base) * 32 + lane;
+    I8OutPre r = {0u, (uint32_t)n};
+    if (n < m.N) {
+        if (m.bias) r.add = __ldg(reinterpret_cast<const unsigned short*>(m.bias) + n);
+        if (!m.clear) r.add |= (uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(m.c) + n) << 16;
+        if (m.c_perm && m.out_invperm) r.kp = __ldg(m.out_invperm + n);
+    }
+    return r;
+}
+__device__ __forceinline__ void finalize_block(const I8Params& P, int blk, int lane, const I8OutPre& pre, float v) {
+    const I8Mat& m = P.mat[mat_of_block(P, blk)];
     const int n = (blk - m.blk_base) * 32 + lane;
     if (n < m.N) {
-        if (m.bias) v += __half2float(m.bias[n]);
-        if (!m.clear) v += __half2float(m.c[n]);
+        v += __half2float(__ushort_as_half((unsigned short)(pre.add & 0xffffu)));          // bias first, then the old value
+        v += __half2float(__ushort_as_half((unsigned short)(pre.add >> 16)));
         const half h = __float2half_rn(v);
         m.c[n] = h;
-        if (m.c_perm) m.c_perm[m.out_invperm ? (int)m.out_invperm[n] : n] = h;
+        if (m.c_perm) m.c_perm[pre.kp] = h;
     }
 }
 
@@ -237,6 +253,11 @@ __device__ __forceinline__ half silu_h(half x) {        // cuda/q_mlp_activation
     const half e = hexp(__hneg(x));
     const half r = hrcp(__hadd(__float2half(1.0f), e));
     return __hmul(x, r);
+}
+__device__ __forceinline__ half2 silu_h2(half2 x) {     // the same op sequence on two values at once (packed fp16 instructions)
+    const half2 e = h2exp(__hneg2(x));
+    const half2 r = h2rcp(__hadd2(__float2half2_rn(1.0f), e));
+    return __hmul2(x, r);
 }
 __device__ __forceinline__ half gelu_h(half x) {        // cuda/q_mlp_activation.cuh:37-47
     float xf = __half2float(x);
@@ -264,66 +285,107 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[I8_WARPS * I8_BARS];
     __shared__ float s_red[I8_WARPS];
-    __shared__ int em_blk[I8_WARPS][2], em_n[I8_WARPS][2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KS = P.KS;
     I8_STAMP(0);
     if (P.dbg_rec && tid == 0) P.dbg_rec[blockIdx.x * 4] = i8_gtimer();
     if (tid < I8_WARPS * I8_BARS) mbar_init(smem_addr(&bars[tid]), 1);
-    if (tid < I8_WARPS * 2) em_blk[tid >> 1][tid & 1] = -1;
     mbar_fence_init();
     __syncthreads();
     griddep_launch_dependents();          // the next launch may become resident (and prefetch ITS weights) right away
 
+    // ---- slot holders.  The grid always has one CTA per SM.  With two launches co-resident per SM, every SM must host exactly
+    //      ONE CTA of every launch of the chain: an SM that has none would offer two free slots to the next launch, which then
+    //      runs two of its CTAs there at half speed each while another SM idles (measured: 10-17 SMs per launch, +50% on the
+    //      launch).  So CTAs without blocks stay resident until the CTAs with blocks are done, then leave with them.
+    if ((int)blockIdx.x >= P.busy_ctas) {
+        if (tid == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(P.slot_cnt) < (unsigned)P.busy_ctas) __nanosleep(200);
+            if (atomicAdd(P.slot_cnt, 1u) == gridDim.x - 1u) *reinterpret_cast<volatile unsigned int*>(P.slot_cnt) = 0u;
+        }
+        return;
+    }
+
     // ---- this CTA's blocks and this warp's stage list, straight from the host-built plan (nothing here depends on the
-    //      previous launch)
+    //      previous launch).  Descriptors are read through L1 where needed, one stage ahead of their use.
     const uint32_t cinfo = __ldg(P.plan_cta + blockIdx.x);
     const int blk0 = (int)(cinfo & 0xffffu), nb = (int)(cinfo >> 16);
     const uint32_t fw0 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp), fw1 = __ldg(P.plan_first + blockIdx.x * I8_WARPS + warp + 1);
     const uint32_t f0 = fw0 & 0x3ffffffu, f1 = fw1 & 0x3ffffffu;
     const int nst = (int)(f1 - f0), n_pre = (int)(fw0 >> 26);
+    const uint4* const list = P.plan_desc + f0;
 
     // shared-memory map: generic pointers for the prologue's stores, 32-bit shared-space addresses (`lds*`) for the main loop
-    const I8Smem sm = i8_smem_map(I8_WARPS, P.arena, KS, P.lcap);
+    const I8Smem sm = i8_smem_map(I8_WARPS, P.arena, KS);
     uint8_t* const act_g = smem + sm.act;
     int* const asum_s = reinterpret_cast<int*>(smem + sm.asum);
     float* const ascale_s = reinterpret_cast<float*>(smem + sm.ascale);
     float* const emit_base = reinterpret_cast<float*>(smem + sm.emit);
-    uint4* const list_g = reinterpret_cast<uint4*>(smem + sm.list) + (size_t)warp * P.lcap;
     uint32_t sbase;        // kept opaque: the compiler would otherwise re-derive every shared address from S2R in the loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_addr(smem)));
     const uint32_t ring = sbase + (uint32_t)warp * (uint32_t)P.arena;
     const uint32_t act = sbase + sm.act, asum = sbase + sm.asum, ascale = sbase + sm.ascale;
-    const uint32_t list = sbase + sm.list + (uint32_t)warp * (uint32_t)P.lcap * 16u;
     uint32_t bar0;
     asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_addr(&bars[warp * I8_BARS])));
 
-    for (int i = lane; i < nst; i += 32) list_g[i] = __ldg(P.plan_desc + f0 + i);
-    __syncwarp();
-    I8_STAMP(8);
-
-    auto packed_of = [&](uint32_t mi) -> const uint8_t* { return mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed); };
-    auto wtab_of = [&](uint32_t mi) -> const void* { return mi == 0 ? P.mat[0].wtab : (mi == 1 ? P.mat[1].wtab : P.mat[2].wtab); };
-    auto issue_stage = [&](int s) {          // lane 0: request stage s into its place in the arena
-        const uint4 d = lds128(list + (uint32_t)s * 16u);
-        const uint32_t bytes = ((d.z >> 11) & 7u) * ((d.z >> 14) & 15u) * 128u;
-        const uint32_t bar = bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u;
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_copy_g2s(ring + ((d.w >> 16) & 0xffu) * 128u, packed_of((d.z >> 22) & 3u) + d.x, bytes, bar);
+    // per-matrix base pointers of the current matrix (a launch fuses up to 3; a warp changes matrix at most twice)
+    uint32_t mi_cur = 0u;
+    const uint8_t* pk_cur = P.mat[0].packed;
+    const uint8_t* wt_cur = reinterpret_cast<const uint8_t*>(P.mat[0].wtab);
+    auto select_mat = [&](uint32_t mi) {          // warp-uniform
+        if (mi != mi_cur) {
+            mi_cur = mi;
+            pk_cur = mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed);
+            wt_cur = reinterpret_cast<const uint8_t*>(mi == 0 ? P.mat[0].wtab : (mi == 1 ? P.mat[1].wtab : P.mat[2].wtab));
+        }
+    };
+    // request stages [s0, s0 + cnt) into their places in the arena: lane j decodes and issues stage s0 + j (cnt <= I8_BARS), so
+    // a batch of requests costs one descriptor decode, not one per stage.  `d` is lane j's descriptor (stage s0 + j), loaded by
+    // the caller well ahead of the request.
+    auto issue_stages = [&](int s0, int cnt, uint4 d) {
+        if (lane < cnt) {
+            const int s = s0 + lane;
+            const uint32_t mi = (d.z >> 22) & 3u;
+            const uint8_t* pk = mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed);
+            const uint32_t bytes = ((d.z >> 24) & 0xffu) << 7;
+            const uint32_t bar = bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u;
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_copy_g2s(ring + ((d.w >> 16) & 0xffu) * 128u, pk + d.x, bytes, bar);
+        }
+    };
+    auto load_req = [&](int s0) -> uint4 {          // lane j's descriptor of stage s0 + j (the next candidates for a request)
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < I8_BARS && s0 + lane < nst) d = __ldg(list + s0 + lane);
+        return d;
     };
     // scale (and GPTQ zero point) of the group a stage belongs to, for this lane's column
     auto fetch_scale = [&](uint4 d) -> uint32_t {
-        const void* t = wtab_of((d.z >> 22) & 3u);
+        select_mat((d.z >> 22) & 3u);
         const uint32_t idx = d.y + (uint32_t)lane;
-        return (d.z & (DF_GPTQ << 18)) ? __ldg(reinterpret_cast<const uint32_t*>(t) + idx)
-                                        : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(t) + idx);
+        return (d.z & (DF_GPTQ << 18)) ? __ldg(reinterpret_cast<const uint32_t*>(wt_cur) + idx)
+                                        : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(wt_cur) + idx);
     };
-    if (lane == 0)
-        for (int i = 0; i < n_pre; ++i) issue_stage(i);
+    uint4 dcur = make_uint4(0u, 0u, 0u, 0u);
+    if (nst > 0) dcur = __ldg(list);
+    I8_STAMP(8);
+    issue_stages(0, n_pre, load_req(0));
     int next_req = n_pre;
+    // EXPERIMENT, off by default (EXL2B_I8_L2PF=1): pull the rest of the warp's share into L2 now (one bulk prefetch per stage),
+    // while the previous launch is still computing.  Measured on B200 it LOSES 6% of the decode step (530 -> 496 tok/s): the
+    // 20-30 MB burst of the next launch competes with the running launch's own refills (profiles/r02_history.md)
+    if (P.l2_prefetch)
+        for (int s0 = n_pre; s0 < nst; s0 += 32) {
+            const int s = s0 + lane;
+            if (s < nst) {
+                const uint4 d = __ldg(list + s);
+                const uint32_t mi = (d.z >> 22) & 3u;
+                const uint8_t* pk = mi == 0 ? P.mat[0].packed : (mi == 1 ? P.mat[1].packed : P.mat[2].packed);
+                bulk_prefetch_l2(pk + d.x, ((d.z >> 24) & 0xffu) << 7);
+            }
+        }
     uint32_t wraw = 0u;
-    if (nst > 0) wraw = fetch_scale(lds128(list));
+    if (nst > 0) wraw = fetch_scale(dcur);
     I8_STAMP(9);
 
     // ---- static operands of the prologue, fetched before the dependency wait: permutation indices (when the row has to be
@@ -338,9 +400,9 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         pv[r] = make_uint4(0, 0, 0, 0);
         wv[r] = make_uint4(0, 0, 0, 0);
         if (o < n_oct) {
-            if (P.perm) pv[r] = __ldg(reinterpret_cast<const uint4*>(P.perm + o * 8));
+            if (P.perm && (gather_x || !P.norm_permuted)) pv[r] = __ldg(reinterpret_cast<const uint4*>(P.perm + o * 8));
             if (P.mode == I8_RMSNORM) {
-                if (P.perm) {
+                if (P.perm && !P.norm_permuted) {
                     const uint16_t* pi = reinterpret_cast<const uint16_t*>(&pv[r]);
                     uint16_t* wo = reinterpret_cast<uint16_t*>(&wv[r]);
 #pragma unroll
@@ -416,7 +478,11 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
                 }
             } else if (P.mode == I8_SILU_MUL) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __half2float(__hmul(silu_h(h[e]), h2[e]));
+                for (int e = 0; e < 8; e += 2) {
+                    const float2 p = __half22float2(__hmul2(silu_h2(__halves2half2(h[e], h[e + 1])), __halves2half2(h2[e], h2[e + 1])));
+                    f[e] = p.x;
+                    f[e + 1] = p.y;
+                }
             } else if (P.mode == I8_GELU_MUL) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = __half2float(__hmul(gelu_h(h[e]), h2[e]));
@@ -467,9 +533,9 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         const int o = ob + tid;
         uint4 pidx = make_uint4(0, 0, 0, 0), wreg = make_uint4(0, 0, 0, 0);
         if (o < n_oct) {
-            if (P.perm) pidx = __ldg(reinterpret_cast<const uint4*>(P.perm + o * 8));
+            if (P.perm && (gather_x || !P.norm_permuted)) pidx = __ldg(reinterpret_cast<const uint4*>(P.perm + o * 8));
             if (P.mode == I8_RMSNORM) {
-                if (P.perm) {
+                if (P.perm && !P.norm_permuted) {
                     const uint16_t* pi = reinterpret_cast<const uint16_t*>(&pidx);
                     uint16_t* wo = reinterpret_cast<uint16_t*>(&wreg);
 #pragma unroll
@@ -496,30 +562,43 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         rrms = rsqrtf(t * (1.0f / (float)P.K) + P.norm_eps);
     }
 
+    // what this warp needs to finish block (warp) of the CTA after the main loop -- who holds its partial sums, where the result goes,
+    // bias / old value for the residual add -- is fetched now, so that the tail of the launch waits for no load
+    uint32_t red0 = 0u;
+    I8OutPre opre0 = {0u, 0u};
+    if (warp < nb) {
+        red0 = __ldg(P.plan_red + blk0 + warp);
+        if (red0 & 0xffffu) opre0 = out_pre(P, blk0 + warp, lane);
+    }
+
     // ---- main loop: this warp alone, stage by stage; everything positional comes from the stage list.
     int am[4] = {0, 0, 0, 0}, ae[2] = {0, 0};
     float tot = 0.f;
     int S = 0, blk_slabs = 0, emits = 0;
 #pragma unroll 1
     for (int s = 0; s < nst; ++s) {
+        const uint4 d = dcur;
+        if (s + 1 < nst) dcur = __ldg(list + s + 1);            // next descriptor: in flight during this stage's arithmetic
+        const uint4 dreq = load_req(next_req);                   // and the ones of the stages this stage's space will be given to
         mbar_wait(bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u, ((uint32_t)s >> 3) & 1u);
-        const uint4 d = lds128(list + (uint32_t)s * 16u);
         const int ks = (int)(d.z & 0x7ffu), n = (int)((d.z >> 11) & 7u), bits = (int)((d.z >> 14) & 15u);
         const uint32_t slot = ring + ((d.w >> 16) & 0xffu) * 128u;
         const uint32_t xs = act + (uint32_t)ks * 64u, as = asum + (uint32_t)ks * 4u;
-        switch (bits) {
-            case 4: S += consume_stage<4>(slot, n, xs, as, lane, am, ae); break;
-            case 5: S += consume_stage<5>(slot, n, xs, as, lane, am, ae); break;
-            case 6: S += consume_stage<6>(slot, n, xs, as, lane, am, ae); break;
-            case 3: S += consume_stage<3>(slot, n, xs, as, lane, am, ae); break;
-            case 8: S += consume_stage<8>(slot, n, xs, as, lane, am, ae); break;
-            default: S += consume_stage<2>(slot, n, xs, as, lane, am, ae); break;
+        {   // dispatch on the bit width as a chain of warp-uniform branches, most frequent first.  (`opaque` keeps the compiler from
+            // fusing the chain into a jump table: BRX through a constant-bank table costs a dependent LDC per stage)
+            int bsel = bits;
+            auto opaque = [&]() { asm volatile("" : "+r"(bsel)); return bsel; };
+            if (bsel == 4) S += consume_stage<4>(slot, n, xs, as, lane, am, ae);
+            else if (opaque() == 5) S += consume_stage<5>(slot, n, xs, as, lane, am, ae);
+            else if (opaque() == 6) S += consume_stage<6>(slot, n, xs, as, lane, am, ae);
+            else if (opaque() == 3) S += consume_stage<3>(slot, n, xs, as, lane, am, ae);
+            else if (opaque() == 8) S += consume_stage<8>(slot, n, xs, as, lane, am, ae);
+            else S += consume_stage<2>(slot, n, xs, as, lane, am, ae);
         }
         __syncwarp();
         {                                          // the space this stage occupied is free: request the stages waiting for it
             const int nreq = (int)((d.w >> 24) & 15u);
-            if (lane == 0)
-                for (int j = 0; j < nreq; ++j) issue_stage(next_req + j);
+            issue_stages(next_req, nreq, dreq);
             next_req += nreq;
         }
         blk_slabs += n;
@@ -533,15 +612,14 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
             am[0] = am[1] = am[2] = am[3] = 0;
             ae[0] = ae[1] = 0;
             S = 0;
-            if (s + 1 < nst) wraw = fetch_scale(lds128(list + (uint32_t)(s + 1) * 16u));      // scales of the next group
+            if (s + 1 < nst) wraw = fetch_scale(dcur);      // scales of the next group
             if (d.z & (DF_BLOCK_DONE << 18)) {
                 const int blk = blk0 + (int)(d.w & 0xffffu);
                 if (blk_slabs == KS) {
-                    finalize_block(P, blk, lane, tot * rrms);          // this warp covered the block's whole K by itself
+                    finalize_block(P, blk, lane, out_pre(P, blk, lane), tot * rrms);          // this warp covered the block's whole K by itself
                 } else {
                     if (emits >= 2) __trap();       // a warp's range has at most two partial blocks (its first and its last)
                     emit_base[(warp * 2 + emits) * 32 + lane] = tot;
-                    if (lane == 0) { em_blk[warp][emits] = blk; em_n[warp][emits] = blk_slabs; }
                     ++emits;
                 }
                 tot = 0.f;
@@ -553,23 +631,21 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     __syncthreads();
     I8_STAMP(5);
 
-    // ---- split-K never left the CTA: sum the warps' partials of each block in warp order, finalise
+    // ---- split-K never left the CTA: sum the warps' partials of each block in warp order (the plan says which warps hold them),
+    //      finalise.  Blocks covered by one warp alone were finalised in the main loop (no partials).
     for (int b = warp; b < nb; b += I8_WARPS) {
-        const int blk = blk0 + b;
-        float v = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int w = 0; w < I8_WARPS; ++w)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (em_blk[w][e] == blk) {
-                    v += emit_base[(w * 2 + e) * 32 + lane];
-                    cnt += em_n[w][e];
-                }
-        if (cnt == 0) continue;          // finalised by the one warp that covered it
-        if (cnt != KS) __trap();
-        finalize_block(P, blk, lane, v * rrms);
+        const uint32_t rd = (b == warp) ? red0 : __ldg(P.plan_red + blk0 + b);
+        uint32_t m = rd & 0xffffu;
+        if (m == 0u) continue;
+        int w = __ffs(m) - 1;
+        float v = emit_base[(w * 2 + (int)((rd >> 16) & 1u)) * 32 + lane];
+        for (m &= m - 1u; m; m &= m - 1u) {
+            w = __ffs(m) - 1;
+            v += emit_base[(w * 2) * 32 + lane];
+        }
+        finalize_block(P, blk0 + b, lane, (b == warp) ? opre0 : out_pre(P, blk0 + b, lane), v * rrms);
     }
+    if (tid == 0 && atomicAdd(P.slot_cnt, 1u) == gridDim.x - 1u) *reinterpret_cast<volatile unsigned int*>(P.slot_cnt) = 0u;
     if (P.dbg && lane == 0) atomicMax(P.dbg + 7, i8_gtimer());
     if (P.dbg_rec && tid == 0) {
         unsigned smid;
@@ -638,6 +714,28 @@ void i8_partition_blocks(const std::vector<uint32_t>& bytes, int ctas, unsigned 
     *used = c;
 }
 
+// RMSNorm weight in a matrix' stored-row order, cached on the matrix (first use: one tiny gather kernel; never inside a capture)
+__global__ void gather_rows_kernel(half* __restrict__ out, const half* __restrict__ w, const uint16_t* __restrict__ perm, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) out[i] = w[perm[i]];
+}
+static std::mutex g_normp_mutex;
+static int i8_permuted_norm(QMatrix* q, const half* norm_w, cudaStream_t stream, const half** out) {
+    std::lock_guard<std::mutex> lk(g_normp_mutex);
+    if (q->normp_src != norm_w) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        if (cs != cudaStreamCaptureStatusNone) { *out = nullptr; return 0; }      // first seen inside a capture: gather in the kernel instead
+        if (!q->normp_buf) EXL2B_CUDA(cudaMalloc(&q->normp_buf, (size_t)q->v.K * sizeof(half)));
+        gather_rows_kernel<<<(q->v.K + 255) / 256, 256, 0, stream>>>(q->normp_buf, norm_w, q->v.perm, q->v.K);
+        g_launch_count++;
+        EXL2B_CUDA(cudaGetLastError());
+        q->normp_src = norm_w;
+    }
+    *out = q->normp_buf;
+    return 0;
+}
+
 // ---- launch plans -------------------------------------------------------------------------------------------------------
 // Everything positional about a launch (block -> CTA partition, every warp's stage list) depends only on the STRUCTURE of its
 // matrices (K, N, bit-width regions, group sizes), not on their addresses: it is computed here once per structure, uploaded,
@@ -648,6 +746,7 @@ struct I8Plan {
     uint4* d_desc = nullptr;
     uint32_t* d_first = nullptr;
     uint32_t* d_cta = nullptr;
+    uint32_t* d_red = nullptr;
     int ctas = 0, lcap = 0, arena = 0;
 };
 struct I8PlanMat {
@@ -660,11 +759,13 @@ static std::mutex g_plan_mutex;
 
 // stage lists of one launch structure: the same walk for every (CTA, warp) -- units are (block, slab) pairs, CTA-relative
 static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* cta_blk, int C, int warps, int arena,
-                           std::vector<uint4>& desc, std::vector<uint32_t>& first, std::vector<uint32_t>& cta, int* lcap) {
+                           std::vector<uint4>& desc, std::vector<uint32_t>& first, std::vector<uint32_t>& cta, std::vector<uint32_t>& red,
+                           int* lcap) {
     const int KS = mats[0].KS;
     int blk_base[I8_MAX_MATS + 1] = {0};
     for (int i = 0; i < nm; ++i) blk_base[i + 1] = blk_base[i] + (mats[i].N + 31) / 32;
     *lcap = 1;
+    red.assign(blk_base[nm], 0u);
     for (int c = 0; c < C; ++c) {
         const int blk0 = cta_blk[c], nb = (int)cta_blk[c + 1] - blk0;
         cta.push_back((uint32_t)blk0 | ((uint32_t)nb << 16));
@@ -694,10 +795,29 @@ static void i8_build_lists(const I8PlanMat* mats, int nm, const unsigned short* 
                 uint4 d;
                 d.x = (uint32_t)bim * m.blk_stream_bytes + rg.off_base + (uint32_t)rel * 128u * (uint32_t)rg.bits;
                 d.y = (uint32_t)(rg.group_base + g) * (uint32_t)m.N + (uint32_t)bim * 32u;
-                d.z = (uint32_t)ks | ((uint32_t)n << 11) | ((uint32_t)rg.bits << 14) | (flags << 18) | ((uint32_t)mi << 22);
+                d.z = (uint32_t)ks | ((uint32_t)n << 11) | ((uint32_t)rg.bits << 14) | (flags << 18) | ((uint32_t)mi << 22) |
+                      ((uint32_t)(n * rg.bits) << 24);          // (bytes / 128 <= 32)
                 d.w = (uint32_t)b;
                 desc.push_back(d);
                 lin += n;
+            }
+            // partial sums this warp leaves in shared memory (the kernel's `emits` counter, replayed): per block the set of such warps
+            // and which of its two partial slots the first one uses (every later warp starts inside the block: slot 0)
+            {
+                int slabs = 0, emits = 0;
+                for (size_t s = first.back(); s < desc.size(); ++s) {
+                    const uint4& d = desc[s];
+                    slabs += (int)((d.z >> 11) & 7u);
+                    if (((d.z >> 18) & 15u) & DF_BLOCK_DONE) {
+                        if (slabs != KS) {
+                            uint32_t& r = red[blk0 + (int)(d.w & 0xffffu)];
+                            if ((r & 0xffffu) == 0) r = (uint32_t)emits << 16;          // the first warp may be on its second partial
+                            r |= 1u << w;
+                            ++emits;
+                        }
+                        slabs = 0;
+                    }
+                }
             }
             // place the warp's stages in its byte arena (a ring): `req` of stage c = how many later stages may be requested once c
             // has been consumed; n_pre = how many are requested up front.  At most I8_BARS stages are ever in flight.
@@ -757,16 +877,16 @@ static int i8_get_plan(int device, const I8PlanMat* mats, int nm, int sms, int w
     unsigned short cta_blk[I8_MAX_CTAS + 1];
     i8_partition_blocks(blk_bytes, sms, cta_blk, &pl.ctas);
     // two launches co-resident per SM (227 KB, 1 KB reserved per CTA) is what lets the next launch prefetch: a CTA gets at most
-    // 112 KB (EXL2B_I8_SMEM overrides), and what the staged row / lists leave of it is split into the warps' weight arenas
-    static const int smem_budget = [] { const char* e = getenv("EXL2B_I8_SMEM"); return e ? atoi(e) : 112 * 1024; }();
+    // 111 KB of dynamic shared memory (EXL2B_I8_SMEM overrides), and what the staged row / lists leave of it is split into the warps' weight arenas
+    static const int smem_budget = [] { const char* e = getenv("EXL2B_I8_SMEM"); return e ? atoi(e) : 111 * 1024; }();
     std::vector<uint4> desc;
-    std::vector<uint32_t> first, cta;
+    std::vector<uint32_t> first, cta, red;
     pl.arena = 8192;
     for (;;) {
         desc.clear(); first.clear(); cta.clear();
-        i8_build_lists(mats, nm, cta_blk, pl.ctas, warps, pl.arena, desc, first, cta, &pl.lcap);
-        if ((int)i8_smem_map(warps, pl.arena, mats[0].KS, pl.lcap).total <= smem_budget || pl.arena <= 2048) break;
-        pl.arena -= 256;
+        i8_build_lists(mats, nm, cta_blk, pl.ctas, warps, pl.arena, desc, first, cta, red, &pl.lcap);
+        if ((int)i8_smem_map(warps, pl.arena, mats[0].KS).total <= smem_budget || pl.arena <= 2048) break;
+        pl.arena -= 128;
     }
     EXL2B_REQUIRE(desc.size() < (1u << 26), "too many stages");
     EXL2B_CUDA(cudaMalloc(&pl.d_desc, desc.size() * sizeof(uint4) + 16));
@@ -775,6 +895,8 @@ static int i8_get_plan(int device, const I8PlanMat* mats, int nm, int sms, int w
     EXL2B_CUDA(cudaMemcpy(pl.d_desc, desc.data(), desc.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     EXL2B_CUDA(cudaMemcpy(pl.d_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
     EXL2B_CUDA(cudaMemcpy(pl.d_cta, cta.data(), cta.size() * 4, cudaMemcpyHostToDevice));
+    EXL2B_CUDA(cudaMalloc(&pl.d_red, red.size() * 4 + 4));
+    EXL2B_CUDA(cudaMemcpy(pl.d_red, red.data(), red.size() * 4, cudaMemcpyHostToDevice));
     g_plans[device][key] = pl;
     *out = pl;
     return 0;
@@ -813,6 +935,12 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.norm_eps = in.norm_eps;
     P.mode = in.mode;
     P.x_permuted = in.x_permuted;
+    if (in.mode == I8_RMSNORM && P.perm) {
+        const half* wp = nullptr;
+        int rcn = i8_permuted_norm(const_cast<QMatrix*>(outs[0].q), in.norm_w, stream, &wp);
+        if (rcn) return rcn;
+        if (wp) { P.norm_w = wp; P.norm_permuted = 1; }
+    }
     I8PlanMat pm[I8_MAX_MATS];
     memset(pm, 0, sizeof(pm));
     int blk = 0;
@@ -850,9 +978,12 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.plan_desc = pl.d_desc;
     P.plan_first = pl.d_first;
     P.plan_cta = pl.d_cta;
-    P.lcap = pl.lcap;
+    P.plan_red = pl.d_red;
     P.arena = pl.arena;
-    const size_t smem_total = i8_smem_map(warps, P.arena, P.KS, P.lcap).total;
+    P.busy_ctas = pl.ctas;
+    static const int l2pf = [] { const char* e = getenv("EXL2B_I8_L2PF"); return e ? atoi(e) : 0; }();
+    P.l2_prefetch = l2pf;
+    const size_t smem_total = i8_smem_map(warps, P.arena, P.KS).total;
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes, K = %d)", smem_total, P.K);
     extern unsigned long long* g_dbg;
     extern int g_dbg_cta, g_dbg_slot;
@@ -860,7 +991,15 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.dbg_cta = g_dbg_cta;
     extern unsigned long long* g_dbg_rec;
     P.dbg_rec = (g_dbg_rec && P.dbg) ? g_dbg_rec + (size_t)((g_dbg_slot - 1) % 64) * I8_MAX_CTAS * 4 : nullptr;
-    const int C = pl.ctas;
+    // one CTA per SM, always (slot holders, see the kernel); a self-resetting counter per launch in flight
+    static unsigned int* slot_cnts[64] = {nullptr};
+    static std::atomic<unsigned> launch_seq{0};
+    if (!slot_cnts[device]) {
+        EXL2B_CUDA(cudaMalloc(&slot_cnts[device], 128 * sizeof(unsigned int)));
+        EXL2B_CUDA(cudaMemset(slot_cnts[device], 0, 128 * sizeof(unsigned int)));
+    }
+    P.slot_cnt = slot_cnts[device] + (launch_seq.fetch_add(1) % 127u);
+    const int C = std::max(pl.ctas, std::min(device_sm_count(device), I8_MAX_CTAS));
     if (warps == 16) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
     else if (warps == 12) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
     else EXL2B_CUDA(launch_pdl(gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
@@ -881,7 +1020,8 @@ extern "C" int exl2b_debug_partition(const uint32_t* block_bytes, int num_blocks
 // given regions (5 ints each: ks_begin, bits, spg_log2, group_base, off_base).  desc: capacity cap_desc x 4 words; first:
 // ctas * warps + 1 words; returns the CTA count in *ctas_used, the descriptor count in *n_desc.
 extern "C" int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_bytes, const int* regions, int num_regions, int ctas, int warps,
-                                int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap) {
+                                int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap,
+                                uint32_t* red) {
     EXL2B_REQUIRE(regions && desc && first && ctas_used && n_desc && lcap, "null argument");
     EXL2B_REQUIRE(num_regions >= 1 && num_regions <= exl2b::MAX_REGIONS && ctas > 0 && ctas <= exl2b::I8_MAX_CTAS && warps > 0, "bad argument");
     exl2b::I8PlanMat m;
@@ -893,11 +1033,12 @@ extern "C" int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_
     unsigned short cta_blk[exl2b::I8_MAX_CTAS + 1];
     exl2b::i8_partition_blocks(bb, ctas, cta_blk, ctas_used);
     std::vector<uint4> d;
-    std::vector<uint32_t> f, c;
-    exl2b::i8_build_lists(&m, 1, cta_blk, *ctas_used, warps, slot_bytes, d, f, c, lcap);      // slot_bytes = bytes of a warp's arena
+    std::vector<uint32_t> f, c, r;
+    exl2b::i8_build_lists(&m, 1, cta_blk, *ctas_used, warps, slot_bytes, d, f, c, r, lcap);      // slot_bytes = bytes of a warp's arena
     EXL2B_REQUIRE((int)d.size() <= cap_desc, "descriptor buffer too small (%zu)", d.size());
     memcpy(desc, d.data(), d.size() * sizeof(uint4));
     memcpy(first, f.data(), f.size() * 4);
+    if (red) memcpy(red, r.data(), r.size() * 4);          // [ceil(N / 32)]
     *n_desc = (int)d.size();
     return 0;
 }

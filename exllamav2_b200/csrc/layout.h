@@ -57,8 +57,21 @@ EXL2B_HD constexpr int extra_seg_base(int bits) { return 32 * plane_main(bits); 
 
 // pair slot p (0..15) of a plane with P bits: which word of the lane, and field slot j inside the word
 EXL2B_HD constexpr int pairs_per_word(int P) { return 16 / P; }
-EXL2B_HD constexpr int pair_word(int P, int p) { return p / pairs_per_word(P); }
-EXL2B_HD constexpr int pair_slot(int P, int p) { return p % pairs_per_word(P); }
+// The assignment pair -> (word, slot) is chosen per plane width so that every plane presents the SAME byte order to the integer
+// dot product: masking field position i of word w of ANY plane leaves the four bytes (k0, k0+4, k0+1, k0+5) of one 8-k octet
+// half (k0 = 8*(m>>1) + 2*(m&1) for operand word m), i.e. pairs p0 = 4*(m>>1) + (m&1) and p0 + 2.  The batch-1 GEMV stages the
+// row ONCE in that order and never permutes an operand (gemv_i8.cu):
+//   P = 4: word w, low / high nibbles  <-> m = 2w, 2w+1          (pairs 4w, 4w+2 | 4w+1, 4w+3)
+//   P = 2: word w, field position i    <-> m = 4w + i            P = 1: bit position i <-> m = i        P = 8: word w <-> m = w
+EXL2B_HD constexpr int pair_word(int P, int p) {
+    return P == 4 ? p / 4 : P == 2 ? (p >> 3) : P == 1 ? 0 : /* P == 8 */ 2 * (p >> 2) + (p & 1);
+}
+EXL2B_HD constexpr int pair_slot(int P, int p) {
+    return P == 4 ? p % 4
+         : P == 2 ? 4 * ((p >> 1) & 1) + 2 * ((p & 7) >> 2) + (p & 1)
+         : P == 1 ? 8 * ((p >> 1) & 1) + 2 * (p >> 2) + (p & 1)
+         : /* P == 8 */ (p >> 1) & 1;
+}
 // field e of pair slot j sits at bit  16*e + P*j  of its word
 EXL2B_HD constexpr int field_bit(int P, int j, int e) { return 16 * e + P * j; }
 // extraction: shift the word right by sh, then the field is at in-halfword offset off (off + P <= 10)

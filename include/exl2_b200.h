@@ -172,7 +172,8 @@ int exl2b_debug_partition(const uint32_t* block_bytes, int num_blocks, int ctas,
 int exl2b_debug_set_records(unsigned long long* records);
 /* host-only: the per-warp stage lists of the batch-1 GEMV for one matrix structure (tests/test_i8_emulation.py) */
 int exl2b_debug_plan(int N, int KS, int is_gptq, uint32_t blk_stream_bytes, const int* regions, int num_regions, int ctas, int warps,
-                     int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap);
+                     int slot_bytes, uint32_t* desc, int cap_desc, uint32_t* first, int* ctas_used, int* n_desc, int* lcap,
+                     uint32_t* red);
 
 /* Stand-in for flash_attn_with_kvcache (third-party in the reference, attn.py:602-613): appends the q_len new K/V rows
  * to the paged fp16 cache at [seqlen, seqlen+q_len) and attends causally.  q [batch,q_len,H,hd], k/v_new

@@ -3,7 +3,8 @@ that are pure bookkeeping and that a wrong constant would break silently.
 
 1. consume_slab: for every bit width, compose a 32 k x 32 column block in the tcgen05 layout (layout.h
    compose_lane_words), stage a row of 16-bit integers in the order stage_round writes it (high / low byte planes,
-   bytes of octet j ordered k = 8j + {0,4,1,5} | {2,6,3,7}) and run the kernel's mask / shift / PRMT selectors; the
+   bytes of octet j ordered k = 8j + {0,4,1,5} | {2,6,3,7}) and run the kernel's mask / shift sequence (no operand is permuted:
+   layout.h pair_word / pair_slot give every plane the same byte order); the
    integer sums must equal sum_k a_k q_k exactly.
 2. work split: the host-side block -> CTA partition (whole 32-column blocks per CTA, balanced by bytes).
 """
@@ -21,6 +22,15 @@ def plane_extra(b):
     return {3: 1, 5: 1, 6: 2}.get(b, 0)
 
 
+def pair_word(P, p):
+    return {4: p // 4, 2: p >> 3, 1: 0, 8: 2 * (p >> 2) + (p & 1)}[P]
+
+
+def pair_slot(P, p):
+    return {4: p % 4, 2: 4 * ((p >> 1) & 1) + 2 * ((p & 7) >> 2) + (p & 1), 1: 8 * ((p >> 1) & 1) + 2 * (p >> 2) + (p & 1),
+            8: (p >> 1) & 1}[P]
+
+
 def compose_lane_words(bits, q):
     """q: 32 values of one column (k = 0..31) -> (main words, extra words) exactly as layout.h compose_lane_words."""
     Pm, Pe = plane_main(bits), plane_extra(bits)
@@ -29,24 +39,14 @@ def compose_lane_words(bits, q):
     for i in range(32):
         p, e = i >> 1, i & 1
         fm = int(q[i]) & ((1 << Pm) - 1)
-        ppw = 16 // Pm
-        mw[p // ppw] |= fm << (16 * e + Pm * (p % ppw))
+        mw[pair_word(Pm, p)] |= fm << (16 * e + Pm * pair_slot(Pm, p))
         if Pe:
             fe = (int(q[i]) >> Pm) & ((1 << Pe) - 1)
-            ppw_e = 16 // Pe
-            ew[p // ppw_e] |= fe << (16 * e + Pe * (p % ppw_e))
+            ew[pair_word(Pe, p)] |= fe << (16 * e + Pe * pair_slot(Pe, p))
     return [w & 0xFFFFFFFF for w in mw], [w & 0xFFFFFFFF for w in ew]
 
 
 # ---- gemv_i8.cu --------------------------------------------------------------------------------------------------------
-
-
-def byte_perm(a, b, sel):
-    src = [(a >> (8 * i)) & 0xFF for i in range(4)] + [(b >> (8 * i)) & 0xFF for i in range(4)]
-    out = 0
-    for n in range(4):
-        out |= src[(sel >> (4 * n)) & 0x7] << (8 * n)
-    return out
 
 
 def dp4a(w, x, signed_x):
@@ -76,17 +76,6 @@ def stage_row(a):
     return XH, XL
 
 
-def two_field_operands(XH, XL):
-    YH, YL = [0] * 8, [0] * 8
-    for w in range(2):
-        for i in range(4):
-            a, b, hi = 2 * w, 2 * w + 1, i & 1
-            sel = 0x7351 if (i & 2) else 0x6240
-            YH[w * 4 + i] = byte_perm(XH[2 * a + hi], XH[2 * b + hi], sel)
-            YL[w * 4 + i] = byte_perm(XL[2 * a + hi], XL[2 * b + hi], sel)
-    return YH, YL
-
-
 def consume_slab(bits, mw, ew, XH, XL):
     """One column of consume_slab<BITS>; returns the value the flush computes before the zero-point term."""
     Pm, Pe = plane_main(bits), plane_extra(bits)
@@ -101,32 +90,25 @@ def consume_slab(bits, mw, ew, XH, XL):
             am[3] += dp4a(hi, XL[2 * j + 1], False)
     elif Pm == 8:
         for w in range(8):
-            j = w >> 1
-            sel = 0x7351 if (w & 1) else 0x6240
-            am[0] += dp4a(mw[w], byte_perm(XH[2 * j], XH[2 * j + 1], sel), True)
-            am[1] += dp4a(mw[w], byte_perm(XL[2 * j], XL[2 * j + 1], sel), False)
+            am[0] += dp4a(mw[w], XH[w], True)
+            am[1] += dp4a(mw[w], XL[w], False)
     else:
-        YH, YL = two_field_operands(XH, XL)
         for w in range(2):
             for i in range(4):
                 t = (mw[w] >> (2 * i)) & 0x03030303
-                am[0] += dp4a(t, YH[w * 4 + i], True)
-                am[1] += dp4a(t, YL[w * 4 + i], False)
+                am[0] += dp4a(t, XH[w * 4 + i], True)
+                am[1] += dp4a(t, XL[w * 4 + i], False)
     if Pe == 1:
         for i in range(8):
-            oa, ob, t = i >> 2, 2 + (i >> 2), i & 3
-            hi = t & 1
-            sel = 0x7351 if (t & 2) else 0x6240
             f = (ew[0] >> i) & 0x01010101
-            ae[0] += dp4a(f, byte_perm(XH[2 * oa + hi], XH[2 * ob + hi], sel), True)
-            ae[1] += dp4a(f, byte_perm(XL[2 * oa + hi], XL[2 * ob + hi], sel), False)
+            ae[0] += dp4a(f, XH[i], True)
+            ae[1] += dp4a(f, XL[i], False)
     elif Pe == 2:
-        YH, YL = two_field_operands(XH, XL)
         for w in range(2):
             for i in range(4):
                 t = (ew[w] >> (2 * i)) & 0x03030303
-                ae[0] += dp4a(t, YH[w * 4 + i], True)
-                ae[1] += dp4a(t, YL[w * 4 + i], False)
+                ae[0] += dp4a(t, XH[w * 4 + i], True)
+                ae[1] += dp4a(t, XL[w * 4 + i], False)
     hi16 = (am[2] << 8) + am[3]
     assert hi16 % 16 == 0
     return ((am[0] << 8) + am[1]) + (hi16 >> 4) + (((ae[0] << 8) + ae[1]) << Pm)
@@ -237,7 +219,7 @@ def _plan(N, KS, regions, ctas=148, warps=16, slot=6144, gptq=0):
     f = ext_c.lib.exl2b_debug_plan
     f.restype = ctypes.c_int
     f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                  ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                  ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     # regions: (ks_begin, bits, spg_log2); group_base / off_base derived like qmatrix.cu build_regions
     reg, gbase, off = [], 0, 0
     for i, (ks0, bits, lg) in enumerate(regions):
@@ -251,10 +233,11 @@ def _plan(N, KS, regions, ctas=148, warps=16, slot=6144, gptq=0):
     desc = np.zeros((cap, 4), dtype=np.uint32)
     first = np.zeros(ctas * warps + 2, dtype=np.uint32)
     used, nd, lcap = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    red = np.zeros((N + 31) // 32, dtype=np.uint32)
     rc = f(N, KS, gptq, stream_bytes, ra.ctypes.data, len(regions), ctas, warps, slot, desc.ctypes.data, cap, first.ctypes.data,
-           ctypes.byref(used), ctypes.byref(nd), ctypes.byref(lcap))
+           ctypes.byref(used), ctypes.byref(nd), ctypes.byref(lcap), red.ctypes.data)
     assert rc == 0
-    return desc[: nd.value], first[: used.value * warps + 1], used.value, lcap.value, stream_bytes, reg
+    return desc[: nd.value], first[: used.value * warps + 1], used.value, lcap.value, stream_bytes, reg, red
 
 
 PLAN_CASES = [
@@ -265,13 +248,15 @@ PLAN_CASES = [
     ("8-bit g32 + 2-bit g64", 512, 64, [(0, 8, 0), (5, 2, 1)]),
     ("g256", 1024, 64, [(0, 4, 3)]),
     ("ragged columns", 1000, 16, [(0, 3, 0), (3, 2, 2)]),
+    ("fewer slabs than warps", 64, 8, [(0, 4, 2)]),
 ]
 
 
 @pytest.mark.parametrize("name,N,KS,regions", PLAN_CASES, ids=[c[0] for c in PLAN_CASES])
 @pytest.mark.parametrize("warps,slot", [(16, 6144), (12, 4096), (16, 2048)])
 def test_stage_lists(name, N, KS, regions, warps, slot):
-    desc, first, C, lcap, stream_bytes, reg = _plan(N, KS, regions, warps=warps, slot=slot)
+    desc, first, C, lcap, stream_bytes, reg, red = _plan(N, KS, regions, warps=warps, slot=slot)
+    partials = {}          # block -> [(warp, partial slot)] as the kernel's main loop leaves them
     nblk = (N + 31) // 32
     seen = np.zeros((nblk, KS), dtype=np.int32)
     n_pre_all = (first >> 26).astype(int)
@@ -308,6 +293,7 @@ def test_stage_lists(name, N, KS, regions, warps, slot):
                     requested += 1
             assert requested == len(lst)
             prev = None
+            blk_slabs = emits = 0
             for i, (x, y, z, bw) in enumerate(lst):
                 ks, n, bits, flags, mi = z & 0x7FF, (z >> 11) & 7, (z >> 14) & 15, (z >> 18) & 15, (z >> 22) & 3
                 blk = bounds[c] + int(bw & 0xFFFF)
@@ -331,4 +317,21 @@ def test_stage_lists(name, N, KS, regions, warps, slot):
                 assert bool(flags & 1) == group_closes, "flush flag"
                 assert bool(flags & 2) == (last or ks + n == KS), "block-done flag"
                 assert not (flags & 4)
+                blk_slabs += n
+                if flags & 2:
+                    if blk_slabs != KS:
+                        assert emits < 2
+                        partials.setdefault(blk, []).append((w, emits))
+                        emits += 1
+                    blk_slabs = 0
     assert np.all(seen == 1), "every (block, slab) exactly once"
+    # the table the launch's tail reads: the warps that hold a partial sum of each block, and the first one's slot
+    for blk in range(nblk):
+        ps = partials.get(blk, [])
+        mask = 0
+        for (w, _) in ps:
+            mask |= 1 << w
+        assert int(red[blk]) & 0xFFFF == mask
+        if ps:
+            assert (int(red[blk]) >> 16) & 1 == ps[0][1] and all(sl == 0 for (_, sl) in ps[1:])
+            assert [w for (w, _) in ps] == sorted(w for (w, _) in ps)

@@ -43,7 +43,8 @@ for i, r in enumerate(rows):
     gs, ge = r[6] - rows[0][6], r[7] - rows[0][6]
     c = [x - rows[0][6] if x else None for x in r[0:6]]
     print(f"{i:3d} {nm:7s} grid {gs/1e3:8.2f} -> {ge/1e3:8.2f} us  dur {(ge-gs)/1e3:6.2f}  gap_from_prev_end {((gs-prev_end)/1e3 if prev_end is not None else 0):6.2f}  cta0 "
-          + " ".join("   -  " if x is None else f"{x/1e3:7.2f}" for x in c))
+          + " ".join("   -  " if x is None else f"{x/1e3:7.2f}" for x in c)
+          + ("  [8,9] " + " ".join(f"{(x - rows[0][6])/1e3:7.2f}" for x in r[8:10] if x) if any(r[8:10]) else ""))
     prev_end = ge
 print("step span us", (rows[-1][7] - rows[0][6]) / 1e3)
 # per-CTA view of the GEMV launches: how many SMs host two CTAs of the SAME launch, spread of the CTAs' compute time

@@ -6,9 +6,12 @@ cub = sys.argv[3] if len(sys.argv) > 3 else "gemv_i8"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 50
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "exllamav2_b200", "libexl2b200.so")], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if cub in f and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+if os.environ.get("CUBIN"):          # a cubin saved from the build the report was taken with
+    cubin_path = os.environ["CUBIN"]
+else:
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "exllamav2_b200", "libexl2b200.so")], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    cubin_path = os.path.join(tmp, [f for f in os.listdir(tmp) if cub in f and f.endswith(".cubin")][0])
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin_path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 seq, cur, on = [], None, False
 for line in dis.split("\n"):
     if line.startswith(".text."): on = kern in line
@@ -28,7 +31,7 @@ tot = sum(agg.values()); ts = max(1, sum(smp.values()))
 srcs = {}
 def text(k):
     if not k: return ""
-    p = os.path.join(root, "exllamav2_b200", "csrc", k[0])
+    p = os.environ.get("SRC") if (os.environ.get("SRC") and k[0] == os.path.basename(os.environ["SRC"]).split("_")[-2] + "_" + os.path.basename(os.environ["SRC"]).split("_")[-1]) else os.path.join(root, "exllamav2_b200", "csrc", k[0])
     if k[0] not in srcs: srcs[k[0]] = open(p).read().split("\n") if os.path.exists(p) else None
     return srcs[k[0]][k[1] - 1].strip()[:110] if srcs[k[0]] else ""
 print(f"total warp instructions {tot}, stall samples {ts}")
