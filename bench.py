@@ -217,12 +217,26 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(dev)
     cfg = PRESETS[args.model]()
     t_build = time.time()
-    dec = ExLlamaV2Decoder(cfg, dev, seed=0, batch_size=1, cache_len=1024)
+    ctx = args.context if args.context > 0 else args.prompt_len
+    need = ctx + 2 * (max(3, args.warmup) + args.steps) + 16
+    dec = ExLlamaV2Decoder(cfg, dev, seed=0, batch_size=1, cache_len=max(1024, (need + 255) // 256 * 256))
     torch.cuda.synchronize()
     t_build = time.time() - t_build
     g = torch.Generator(device="cpu").manual_seed(0)
     prompt = torch.randint(0, cfg.vocab_size, (1, args.prompt_len), generator=g).to(dev)
-    dec.prefill(prompt)
+    if args.context > 0:
+        # synthetic cache rows (random nibbles, scales of a unit-variance row): the decode step's cost does not depend on their values
+        gd = torch.Generator(device=dev).manual_seed(1)
+        for li in range(cfg.num_layers):
+            for t in (dec.cache.key_states[li], dec.cache.value_states[li]):
+                t.copy_(torch.randint(0, 256, t.shape, dtype=torch.uint8, device=dev, generator=gd))
+            for t in (dec.cache.key_scales[li], dec.cache.value_scales[li]):
+                t.fill_(0.35)
+        dec.cache.cache_seqlens.fill_(args.context)
+        dec.pos = args.context
+        dec.ids.copy_(prompt[:, -1:])
+    else:
+        dec.prefill(prompt)
     torch.cuda.synchronize()
 
     # graph: decode step + on-device greedy pick feeding the next step (fully device-resident loop)
@@ -256,7 +270,7 @@ def run_ours(args, rank, world):
         print(json.dumps({"profiled_steps": 2}))
         return
     W, K = max(3, args.warmup), args.steps
-    assert args.prompt_len + 2 * (W + K) + 8 < dec.cache.max_seq_len
+    assert ctx + 2 * (W + K) + 8 < dec.cache.max_seq_len
     for _ in range(W):
         graph.replay()
     torch.cuda.synchronize()
@@ -391,7 +405,7 @@ def run_ours(args, rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16 (int2-8 weights, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": f"{cfg.name} single-stream decode, {args.prompt_len}-token prompt, Q4 KV cache, bs=1",
+        "config": {"workload": f"{cfg.name} single-stream decode, " + (f"{args.context}-position synthetic context" if args.context > 0 else f"{args.prompt_len}-token prompt") + ", Q4 KV cache, bs=1",
                    "l2": f"inputs_exceed_l2 ({dec.weight_bytes / 1e9:.2f} GB of weights per step)", "weight_bytes": dec.weight_bytes, "build_s": round(t_build, 1),
                    "quant_plan": {"attn": str(cfg.plan.attn), "mlp (cycled over layers)": str(cfg.plan.mlp), "head": str(cfg.plan.head)}},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
@@ -450,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama2-7b-4.0bpw")
     ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--context", type=int, default=0,
+                    help="decode at this context length: the Q4 cache is filled with synthetic rows up to N positions (no prompt pass); 0 = run the prompt")
     ap.add_argument("--mode", default="decode", choices=["decode", "prefill"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip the reference-extension leg (oracle/_ref on the same GPU)")

@@ -308,26 +308,6 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     AQ_STAMP(3);
-    if (h % group == 0 && z == 0) {
-        for (int idx = tid; idx < 2 * P.q_len * (ROWB / 4); idx += AQ_THREADS) {
-            const int kv = idx / (P.q_len * (ROWB / 4)), r = idx - kv * P.q_len * (ROWB / 4);
-            const int i = r / (ROWB / 4), wd = r - i * (ROWB / 4);
-            const int pos = seqlen + i;
-            const int page = bt[pos / P.page_size];
-            const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
-            reinterpret_cast<uint32_t*>((kv ? P.v_q : P.k_q) + row * ROWB)[wd] =
-                reinterpret_cast<const uint32_t*>(new_q + (kv * AQ_MAX_QLEN + i) * ROWB)[wd];
-        }
-        for (int idx = tid; idx < 2 * P.q_len * NSC; idx += AQ_THREADS) {
-            const int kv = idx / (P.q_len * NSC), r = idx - kv * P.q_len * NSC;
-            const int i = r / NSC, s = r - i * NSC;
-            const int pos = seqlen + i;
-            const int page = bt[pos / P.page_size];
-            const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
-            (kv ? P.v_s : P.k_s)[row * NSC + s] = new_s[(kv * AQ_MAX_QLEN + i) * NSC + s];
-        }
-    }
-
     AQ_STAMP(8);
 
     // score of one 32-value block of a cached row (4-bit values, one fp16 scale) against its block of the rotated query:
@@ -362,15 +342,16 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
             float s = 0.f;
             if (p < n_ctx) {
                 if (p >= seqlen) {               // a row appended by this step: fp16 values, rotated in fp32
-                    const float* y = new_y + (p - seqlen) * HD + kblk * 32;
-                    const float* qb_ = qrot + kblk * QPAD;
+                    const float4* y4 = reinterpret_cast<const float4*>(new_y + (p - seqlen) * HD + kblk * 32);
+                    const float4* q4 = reinterpret_cast<const float4*>(qrot + kblk * QPAD);
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s0 = fmaf(qb_[j], y[j], s0);
-                        s1 = fmaf(qb_[j + 1], y[j + 1], s1);
-                        s2 = fmaf(qb_[j + 2], y[j + 2], s2);
-                        s3 = fmaf(qb_[j + 3], y[j + 3], s3);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = q4[j], c = y4[j];
+                        s0 = fmaf(a.x, c.x, s0);
+                        s1 = fmaf(a.y, c.y, s1);
+                        s2 = fmaf(a.z, c.z, s2);
+                        s3 = fmaf(a.w, c.w, s3);
                     }
                     s = (s0 + s1) + (s2 + s3);
                 } else {
@@ -506,6 +487,27 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_q4_kernel(const __grid_con
         for (int j = 0; j < VEC; ++j) red[warp * HD + lane * VEC + j] = acc[j];
         __syncthreads();
         AQ_STAMP(5);
+        // the rows appended by this step go to the cache now, from shared memory, by the last warp (it has no part in the reduction
+        // below): nothing on the way to the output waits for these stores
+        if (i == P.q_len - 1 && warp == AQ_WARPS - 1 && h % group == 0 && z == 0) {
+            for (int idx = lane; idx < 2 * P.q_len * (ROWB / 4); idx += 32) {
+                const int kv = idx / (P.q_len * (ROWB / 4)), r = idx - kv * P.q_len * (ROWB / 4);
+                const int ii = r / (ROWB / 4), wd = r - ii * (ROWB / 4);
+                const int pos = seqlen + ii;
+                const int page = bt[pos / P.page_size];
+                const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
+                reinterpret_cast<uint32_t*>((kv ? P.v_q : P.k_q) + row * ROWB)[wd] =
+                    reinterpret_cast<const uint32_t*>(new_q + (kv * AQ_MAX_QLEN + ii) * ROWB)[wd];
+            }
+            for (int idx = lane; idx < 2 * P.q_len * NSC; idx += 32) {
+                const int kv = idx / (P.q_len * NSC), r = idx - kv * P.q_len * NSC;
+                const int ii = r / NSC, sidx = r - ii * NSC;
+                const int pos = seqlen + ii;
+                const int page = bt[pos / P.page_size];
+                const size_t row = ((size_t)page * P.page_size + pos % P.page_size) * P.KVH + kvh;
+                (kv ? P.v_s : P.k_s)[row * NSC + sidx] = new_s[(kv * AQ_MAX_QLEN + ii) * NSC + sidx];
+            }
+        }
         // ---- 5. sum over warps, (merge the splits,) rotate back (x = H y / 32), normalise, store ----
         if (ns_act > 1) {
             // leave (unnormalised rotated output, max, sum) of this chunk; the last CTA of the (head, sequence) merges them all

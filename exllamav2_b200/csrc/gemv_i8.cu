@@ -204,6 +204,33 @@ template <int BITS>
 __device__ __forceinline__ int consume_stage(uint32_t slot, int n, uint32_t xs, uint32_t asum, int lane, int (&am)[4], int (&ae)[2]) {
     constexpr uint32_t bb = 128 * BITS;
     int S = 0;
+    if constexpr (BITS == 4) {
+        // the common case: the lane's weight words of slab s + 1 are loaded before the arithmetic of slab s (the shared-memory round
+        // trip of the one non-broadcast load hides behind 16 dot products)
+        uint4 w4 = lds128(slot + lane * 16);
+#pragma unroll 1
+        for (int s = 0; s < n; ++s) {
+            const uint4 wn = lds128(slot + (s + 1 < n ? s + 1 : s) * bb + lane * 16);
+            const uint32_t x = xs + s * 64;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const uint4 xh = lds128(x + hf * 16), xl = lds128(x + 32 + hf * 16);
+                const uint32_t wa = hf ? w4.z : w4.x, wc = hf ? w4.w : w4.y;
+                const uint32_t lo0 = wa & 0x0f0f0f0fu, hi0 = wa & 0xf0f0f0f0u, lo1 = wc & 0x0f0f0f0fu, hi1 = wc & 0xf0f0f0f0u;
+                am[0] = dp4a_us(lo0, xh.x, am[0]);
+                am[1] = dp4a_uu(lo0, xl.x, am[1]);
+                am[2] = dp4a_us(hi0, xh.y, am[2]);
+                am[3] = dp4a_uu(hi0, xl.y, am[3]);
+                am[0] = dp4a_us(lo1, xh.z, am[0]);
+                am[1] = dp4a_uu(lo1, xl.z, am[1]);
+                am[2] = dp4a_us(hi1, xh.w, am[2]);
+                am[3] = dp4a_uu(hi1, xl.w, am[3]);
+            }
+            S += (int)lds32(asum + s * 4);
+            w4 = wn;
+        }
+        return S;
+    }
 #pragma unroll 1
     for (int s = 0; s < n; ++s) {
         consume_slab<BITS>(slot + s * bb, xs + s * 64, lane, am, ae);
@@ -579,6 +606,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     for (int s = 0; s < nst; ++s) {
         const uint4 d = dcur;
         if (s + 1 < nst) dcur = __ldg(list + s + 1);            // next descriptor: in flight during this stage's arithmetic
+        const int nreq = (int)((d.w >> 24) & 15u);
         const uint4 dreq = load_req(next_req);                   // and the ones of the stages this stage's space will be given to
         mbar_wait(bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u, ((uint32_t)s >> 3) & 1u);
         const int ks = (int)(d.z & 0x7ffu), n = (int)((d.z >> 11) & 7u), bits = (int)((d.z >> 14) & 15u);
@@ -597,7 +625,6 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
         }
         __syncwarp();
         {                                          // the space this stage occupied is free: request the stages waiting for it
-            const int nreq = (int)((d.w >> 24) & 15u);
             issue_stages(next_req, nreq, dreq);
             next_req += nreq;
         }

@@ -17,6 +17,9 @@ for SH in qkvo54 gateup54 down43 head; do
   echo "=== ncu full $SH"; timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemv_i8 -s 12 -c 1 -f -o gpurun_out/${T}_gemv_i8_$SH python tools/microbench.py --shapes $SH --m 1 --total-mb 96 2>&1 | tail -1 | cut -c1-200
 done
 echo "=== timeline"; timeout 300 python tools/model_timeline.py 2 > gpurun_out/${T}_timeline.txt 2>&1; tail -14 gpurun_out/${T}_timeline.txt
+for CTX in 1024 4096 16384; do
+  echo "=== decode at context $CTX"; timeout 400 python bench.py --context $CTX --steps 32 --no-cpu --no-ref-ext > gpurun_out/${T}_bench_ctx$CTX.json 2> gpurun_out/${T}_bench_ctx$CTX.err; cut -c1-400 gpurun_out/${T}_bench_ctx$CTX.json; tail -2 gpurun_out/${T}_bench_ctx$CTX.err
+done
 echo "=== prefill"; timeout 600 python bench.py --mode prefill --steps 4 > gpurun_out/${T}_bench_prefill.json 2> gpurun_out/${T}_bench_prefill.err; cut -c1-900 gpurun_out/${T}_bench_prefill.json; tail -3 gpurun_out/${T}_bench_prefill.err
 echo "=== tinyllama"; timeout 600 python bench.py --model tinyllama-1.1b-4.0bpw --steps 64 --no-cpu --no-ref-ext > gpurun_out/${T}_bench_tinyllama.json 2> gpurun_out/${T}_bench_tinyllama.err; cut -c1-600 gpurun_out/${T}_bench_tinyllama.json; tail -2 gpurun_out/${T}_bench_tinyllama.err
 echo "=== gptq 7b"; timeout 600 python bench.py --model llama2-7b-gptq-g128-act --steps 64 --no-cpu --no-ref-ext > gpurun_out/${T}_bench_gptq.json 2> gpurun_out/${T}_bench_gptq.err; cut -c1-600 gpurun_out/${T}_bench_gptq.json; tail -2 gpurun_out/${T}_bench_gptq.err
