@@ -126,8 +126,8 @@ extern "C" int exl2b_paged_attn_decode(const uint16_t* q, const uint16_t* k_new,
     P.scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid(num_heads, batch);
     if (head_dim == 128)
-        EXL2B_CUDA(launch_pdl(attn_decode_kernel<4>, grid, dim3(128), 0, (cudaStream_t)stream, P));
+        EXL2B_CUDA(launch_pdl_f("attn", attn_decode_kernel<4>, grid, dim3(128), 0, (cudaStream_t)stream, P));
     else
-        EXL2B_CUDA(launch_pdl(attn_decode_kernel<2>, grid, dim3(128), 0, (cudaStream_t)stream, P));
+        EXL2B_CUDA(launch_pdl_f("attn", attn_decode_kernel<2>, grid, dim3(128), 0, (cudaStream_t)stream, P));
     return 0;
 }

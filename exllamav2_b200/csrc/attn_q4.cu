@@ -725,10 +725,10 @@ extern "C" int exl2b_paged_attn_decode_q4_ex(const uint16_t* q, const uint16_t* 
     P.slot_cnt = slot_cnts[dev] + (launch_seq.fetch_add(1) % 127u);
     P.batch = batch;
     P.busy_ctas = num_heads * batch * nsplit;
-    dim3 grid(std::max(P.busy_ctas, device_sm_count(dev)));
+    dim3 grid(slot_holders_disabled() ? P.busy_ctas : std::max(P.busy_ctas, device_sm_count(dev)));
     if (head_dim == 128)
-        EXL2B_CUDA(launch_pdl(attn_q4_kernel<128>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
+        EXL2B_CUDA(launch_pdl_f("attn", attn_q4_kernel<128>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
     else
-        EXL2B_CUDA(launch_pdl(attn_q4_kernel<64>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
+        EXL2B_CUDA(launch_pdl_f("attn", attn_q4_kernel<64>, grid, dim3(AQ_THREADS), smem, (cudaStream_t)stream, P));
     return 0;
 }

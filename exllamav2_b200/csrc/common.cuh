@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -36,6 +37,33 @@ extern std::atomic<uint64_t> g_launch_count;
 
 // Launch with Programmatic Dependent Launch enabled: the kernel may start while its predecessor in the stream is
 // still draining; it must call griddep_wait() before touching anything the predecessor writes.
+// EXL2B_NO_PDL=1 (all kernels) or a list of kernel families (i8, tc, attn, small): plain stream-ordered launches (diagnostics)
+inline bool pdl_disabled(const char* family) {
+    static const char* e = getenv("EXL2B_NO_PDL");
+    if (!e) return false;
+    if (e[0] == '1' || e[0] == '\0') return true;
+    return strstr(e, family) != nullptr;
+}
+inline bool slot_holders_disabled() {          // EXL2B_NO_HOLDERS=1: grids of working CTAs only (diagnostics)
+    static const bool off = getenv("EXL2B_NO_HOLDERS") != nullptr;
+    return off;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_f(const char* family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_disabled(family) ? 0 : 1;
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
@@ -48,8 +76,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    static const bool no_pdl = getenv("EXL2B_NO_PDL") != nullptr;     // diagnostics: plain stream-ordered launches
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = pdl_disabled("small") ? 0 : 1;
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

@@ -1032,12 +1032,12 @@ int gemm_tc_launch(int device, cudaStream_t stream, GemvMat* mats, int nm, int M
         if (!prepared) {
             Q.x = mats[0].x + (size_t)m0 * mats[0].ldx;
             Q.M = P.M;
-            EXL2B_CUDA(launch_pdl(tc_prep_kernel, dim3(GEMV_MTOK), dim3(1024), 0, stream, Q));
+            EXL2B_CUDA(launch_pdl_f("tc", tc_prep_kernel, dim3(GEMV_MTOK), dim3(1024), 0, stream, Q));
         }
         if (P.M == 1) {
-            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
+            EXL2B_CUDA(launch_pdl_f("tc", gemm_tc_kernel<1>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
         } else {
-            EXL2B_CUDA(launch_pdl(gemm_tc_kernel<8>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
+            EXL2B_CUDA(launch_pdl_f("tc", gemm_tc_kernel<8>, dim3(grid), dim3(TC_THREADS), smem_total, stream, P));
         }
     }
     return 0;

@@ -1026,10 +1026,10 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
         EXL2B_CUDA(cudaMemset(slot_cnts[device], 0, 128 * sizeof(unsigned int)));
     }
     P.slot_cnt = slot_cnts[device] + (launch_seq.fetch_add(1) % 127u);
-    const int C = std::max(pl.ctas, std::min(device_sm_count(device), I8_MAX_CTAS));
-    if (warps == 16) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
-    else if (warps == 12) EXL2B_CUDA(launch_pdl(gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
-    else EXL2B_CUDA(launch_pdl(gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
+    const int C = slot_holders_disabled() ? pl.ctas : std::max(pl.ctas, std::min(device_sm_count(device), I8_MAX_CTAS));
+    if (warps == 16) EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
+    else if (warps == 12) EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
+    else EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
     return 0;
 }
 

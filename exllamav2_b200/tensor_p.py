@@ -242,6 +242,9 @@ class ExLlamaV2DecoderTP:
 
     def capture(self, body=None):
         body = body or self._decode_step
+        # the warm-up step and the capture run on a side stream over the decoder's static buffers: everything already queued on the
+        # caller's stream (earlier decode steps whose results the caller may not have read yet) has to be finished first
+        torch.cuda.synchronize()
         s = torch.cuda.Stream(self.device)
         saved = self.cache.cache_seqlens.clone()
         with torch.cuda.stream(s):
