@@ -37,7 +37,7 @@
 namespace exl2b {
 
 constexpr int I8_MAX_WARPS = 16;
-constexpr int I8_MAX_CTAS = 160;
+constexpr int I8_MAX_CTAS = 320;
 
 struct I8Mat {
     const uint8_t* packed;
@@ -76,6 +76,7 @@ struct I8Params {
     float norm_eps;
     int mode, x_permuted;
     int norm_permuted;                // norm_w is already in stored-row order (QMatrix::normp_buf)
+    int l1_hints;                     // descriptor loads L1::evict_last, scale loads L1::no_allocate
     int l2_prefetch;                  // prefetch the part of a warp's share that does not fit its arena into L2 before the wait
     int arena;                        // bytes of a warp's weight arena
     int busy_ctas;                    // CTAs that own blocks; the rest of the grid only keeps its SM slot occupied (see the kernel)
@@ -110,6 +111,24 @@ __device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {
     int d;
     asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// descriptor / scale loads with L1 policies: the (small, re-read) stage lists are kept, the (read-once) scale entries pass through.
+// With 222 KB of the SM's 256 KB configured as shared memory the L1 is 28 KB for 32 warps; measured global-load hit rate 40%.
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_pass_u16(const void* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_pass_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 // ---- one slab (32 k) of the warp's 32-column block: integer dot products, one column per lane -------------------------------
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KS = P.KS;
     I8_STAMP(0);
-    if (P.dbg_rec && tid == 0) P.dbg_rec[blockIdx.x * 4] = i8_gtimer();
+    if (P.dbg_rec && tid == 0 && blockIdx.x < 160) P.dbg_rec[blockIdx.x * 4] = i8_gtimer();
     if (tid < I8_WARPS * I8_BARS) mbar_init(smem_addr(&bars[tid]), 1);
     mbar_fence_init();
     __syncthreads();
@@ -383,18 +402,21 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     };
     auto load_req = [&](int s0) -> uint4 {          // lane j's descriptor of stage s0 + j (the next candidates for a request)
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
-        if (lane < I8_BARS && s0 + lane < nst) d = __ldg(list + s0 + lane);
+        if (lane < I8_BARS && s0 + lane < nst) d = P.l1_hints ? ldg_keep(list + s0 + lane) : __ldg(list + s0 + lane);
         return d;
     };
     // scale (and GPTQ zero point) of the group a stage belongs to, for this lane's column
     auto fetch_scale = [&](uint4 d) -> uint32_t {
         select_mat((d.z >> 22) & 3u);
         const uint32_t idx = d.y + (uint32_t)lane;
+        if (P.l1_hints)
+            return (d.z & (DF_GPTQ << 18)) ? ldg_pass_u32(reinterpret_cast<const uint32_t*>(wt_cur) + idx)
+                                            : ldg_pass_u16(reinterpret_cast<const unsigned short*>(wt_cur) + idx);
         return (d.z & (DF_GPTQ << 18)) ? __ldg(reinterpret_cast<const uint32_t*>(wt_cur) + idx)
                                         : (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(wt_cur) + idx);
     };
     uint4 dcur = make_uint4(0u, 0u, 0u, 0u);
-    if (nst > 0) dcur = __ldg(list);
+    if (nst > 0) dcur = P.l1_hints ? ldg_keep(list) : __ldg(list);
     I8_STAMP(8);
     issue_stages(0, n_pre, load_req(0));
     int next_req = n_pre;
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     I8_STAMP(1);
     griddep_wait();                        // everything below may read what the previous launch wrote
     I8_STAMP(2);
-    if (P.dbg_rec && tid == 0) P.dbg_rec[blockIdx.x * 4 + 1] = i8_gtimer();
+    if (P.dbg_rec && tid == 0 && blockIdx.x < 160) P.dbg_rec[blockIdx.x * 4 + 1] = i8_gtimer();
 
     // ---- prologue: the row -> (optional RMSNorm weight / act*mul) -> 16-bit integers per 128-k block -> shared memory.
     //      Every CTA stages the whole row (its blocks span all of K); 1/rms is applied to the finished fp32 sums.
@@ -605,7 +627,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
 #pragma unroll 1
     for (int s = 0; s < nst; ++s) {
         const uint4 d = dcur;
-        if (s + 1 < nst) dcur = __ldg(list + s + 1);            // next descriptor: in flight during this stage's arithmetic
+        if (s + 1 < nst) dcur = P.l1_hints ? ldg_keep(list + s + 1) : __ldg(list + s + 1);      // next descriptor: in flight during this stage
         const int nreq = (int)((d.w >> 24) & 15u);
         const uint4 dreq = load_req(next_req);                   // and the ones of the stages this stage's space will be given to
         mbar_wait(bar0 + ((uint32_t)s & (I8_BARS - 1)) * 8u, ((uint32_t)s >> 3) & 1u);
@@ -674,7 +696,7 @@ __global__ void __launch_bounds__(I8_WARPS * 32, 2) gemv_i8_kernel(const __grid_
     }
     if (tid == 0 && atomicAdd(P.slot_cnt, 1u) == gridDim.x - 1u) *reinterpret_cast<volatile unsigned int*>(P.slot_cnt) = 0u;
     if (P.dbg && lane == 0) atomicMax(P.dbg + 7, i8_gtimer());
-    if (P.dbg_rec && tid == 0) {
+    if (P.dbg_rec && tid == 0 && blockIdx.x < 160) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         P.dbg_rec[blockIdx.x * 4 + 2] = i8_gtimer();
@@ -1000,7 +1022,14 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     }
     EXL2B_REQUIRE(P.KS <= 2048, "K = %d exceeds the stage descriptor (K <= 65536)", P.K);
     I8Plan pl;
-    int rc = i8_get_plan(device, pm, nm, std::min(device_sm_count(device), I8_MAX_CTAS), warps, &pl);
+    // EXPERIMENT (EXL2B_I8_DOUBLE_MB=n, off by default): launches of at least n MB use BOTH slots of every SM themselves (twice the
+    // CTAs, half the work each: 32 warps per SM on one launch) instead of leaving one to the next launch's prefetch
+    static const int double_mb = [] { const char* e = getenv("EXL2B_I8_DOUBLE_MB"); return e ? atoi(e) : 0; }();
+    unsigned long long launch_bytes = 0;
+    for (int i = 0; i < nm; ++i) launch_bytes += outs[i].q->packed_bytes;
+    const int slots = (double_mb > 0 && launch_bytes >= (unsigned long long)double_mb << 20) ? 2 : 1;
+    const int grid_ctas = std::min(device_sm_count(device) * slots, I8_MAX_CTAS);
+    int rc = i8_get_plan(device, pm, nm, grid_ctas, warps, &pl);
     if (rc) return rc;
     P.plan_desc = pl.d_desc;
     P.plan_first = pl.d_first;
@@ -1010,6 +1039,8 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.busy_ctas = pl.ctas;
     static const int l2pf = [] { const char* e = getenv("EXL2B_I8_L2PF"); return e ? atoi(e) : 0; }();
     P.l2_prefetch = l2pf;
+    static const int l1h = [] { const char* e = getenv("EXL2B_I8_L1HINT"); return e ? atoi(e) : 0; }();
+    P.l1_hints = l1h;
     const size_t smem_total = i8_smem_map(warps, P.arena, P.KS).total;
     EXL2B_REQUIRE(smem_total <= 200 * 1024, "shared memory budget exceeded (%zu bytes, K = %d)", smem_total, P.K);
     extern unsigned long long* g_dbg;
@@ -1017,7 +1048,7 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
     P.dbg = g_dbg ? g_dbg + 32 * (g_dbg_slot++ % 64) : nullptr;
     P.dbg_cta = g_dbg_cta;
     extern unsigned long long* g_dbg_rec;
-    P.dbg_rec = (g_dbg_rec && P.dbg) ? g_dbg_rec + (size_t)((g_dbg_slot - 1) % 64) * I8_MAX_CTAS * 4 : nullptr;
+    P.dbg_rec = (g_dbg_rec && P.dbg) ? g_dbg_rec + (size_t)((g_dbg_slot - 1) % 64) * 160 * 4 : nullptr;      // [64][160][4], CTAs 0..159
     // one CTA per SM, always (slot holders, see the kernel); a self-resetting counter per launch in flight
     static unsigned int* slot_cnts[64] = {nullptr};
     static std::atomic<unsigned> launch_seq{0};
@@ -1026,7 +1057,7 @@ int gemv_i8_launch(int device, cudaStream_t stream, const I8Out* outs, int nm, c
         EXL2B_CUDA(cudaMemset(slot_cnts[device], 0, 128 * sizeof(unsigned int)));
     }
     P.slot_cnt = slot_cnts[device] + (launch_seq.fetch_add(1) % 127u);
-    const int C = slot_holders_disabled() ? pl.ctas : std::max(pl.ctas, std::min(device_sm_count(device), I8_MAX_CTAS));
+    const int C = slot_holders_disabled() ? pl.ctas : std::max(pl.ctas, grid_ctas);
     if (warps == 16) EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<16>, dim3(C), dim3(16 * 32), smem_total, stream, P));
     else if (warps == 12) EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<12>, dim3(C), dim3(12 * 32), smem_total, stream, P));
     else EXL2B_CUDA(launch_pdl_f("i8", gemv_i8_kernel<8>, dim3(C), dim3(8 * 32), smem_total, stream, P));
