@@ -470,6 +470,9 @@ def q_mlp_forward_(q_mlp: int, x, loras=(), loras_temp=none_tensor):
     _dtype(x, torch.float16, "x")
     temp_a, temp_b = _mlp_temps[q_mlp]
     rows = x.numel() // x.shape[-1]
+    if rows > temp_a.shape[0]:          # the reference sizes temp_a / temp_b for max_rows at make_q_mlp time and would write past them
+        raise RuntimeError(f"q_mlp_forward_: {rows} rows exceed the {temp_a.shape[0]} rows of temp_a given to make_q_mlp "
+                           "(use q_mlp_forward_rows with scratch of your own for larger chunks)")
     _check(lib.exl2b_qmlp_forward(q_mlp, x.data_ptr(), rows, temp_a.data_ptr(), _p(temp_b), _stream(x)))
 
 

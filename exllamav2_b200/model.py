@@ -190,7 +190,7 @@ class ExLlamaV2Decoder:
         self.weight_bytes = 0          # algorithmic bytes of all linears for one token
         self.layers: list[_Layer] = []
         self.linears: list[ExLlamaV2Linear] = []
-        max_rows = 64
+        max_rows = max(64, 8 * batch_size)          # rows of one call through the block functions (their temp buffers): 8 tokens per sequence
 
         def lin(K, N, plan, s, perm_seed=None):
             w = synthetic.random_linear(K, N, plan, device=dev, seed=s, weight_std=1.0 / math.sqrt(K), perm_seed=perm_seed)
@@ -224,8 +224,9 @@ class ExLlamaV2Decoder:
         self.final_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
         self.lm_head = lin(hid, cfg.vocab_size, cfg.plan.head, s + 9)
         self.embed = (0.02 * torch.randn((cfg.vocab_size, hid), device=dev, generator=gen)).half()
-        self.sin, self.cos = rope_tables(hd, cfg.max_seq_len, cfg.rope_theta, dev)
+        # one table row per cache position: the fused / stand-alone RoPE kernels index the tables by position and cannot see their length
         cache_len = cache_len or min(cfg.max_seq_len, 1024)
+        self.sin, self.cos = rope_tables(hd, max(cfg.max_seq_len, (cache_len + 255) // 256 * 256), cfg.rope_theta, dev)
         self.cache = ExLlamaV2Cache_Q4(cfg, batch_size, cache_len, dev)
         self.batch_size = batch_size
         # static decode buffers (graph-capturable)

@@ -171,8 +171,8 @@ class ExLlamaV2DecoderTP:
         self.final_norm = (1 + 0.1 * torch.randn((hid,), device=dev, generator=gen)).half()
         self.lm_head = lin(hid, cfg.vocab_size, cfg.plan.head, s + 9, tp.mine(tp.vc))
         self.embed = (0.02 * torch.randn((cfg.vocab_size, hid), device=dev, generator=gen)).half()
-        self.sin, self.cos = rope_tables(hd, cfg.max_seq_len, cfg.rope_theta, dev)
         cache_len = cache_len or min(cfg.max_seq_len, 1024)
+        self.sin, self.cos = rope_tables(hd, max(cfg.max_seq_len, (cache_len + 255) // 256 * 256), cfg.rope_theta, dev)
         local_cfg = LlamaConfig(cfg.name, hid, inter, self.Hl, self.KVHl, hd, cfg.num_layers, cfg.vocab_size, cfg.max_seq_len)
         self.cache = ExLlamaV2Cache_Q4(local_cfg, batch_size, cache_len, dev)        # this rank's kv heads
         self.batch_size = B = batch_size
@@ -372,7 +372,7 @@ def run_bench(args, rank: int, world: int, metric: str, unit: str):
             "clocks": clk.summary(),
             "e2e": {"value": 1.0 / t_e2e, "unit": unit, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": cfg.vocab_size * 2, "ms_per_step": t_e2e * 1e3},
             "gpu_launches": int(launches_per_step * K * world), "launches_per_step": int(launches_per_step),
-            "roofline": {"bound": "hbm", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "gemv_i8_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "note": "per-GPU algorithmic weight bytes / whole step time (collectives and attention included): a lower bound on the kernel's own rate"},
             "cpu_baseline": None,
