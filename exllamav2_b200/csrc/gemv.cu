@@ -100,7 +100,10 @@ extern "C" int exl2b_gemm_half_q_half(exl2b_qmatrix_t h, const uint16_t* a, int 
         const I8Input in = {(const half*)a, nullptr, nullptr, 0.f, I8_PLAIN};
         return gemv_i8_launch(q->device, (cudaStream_t)stream, &o, 1, in);
     }
-    if ((m > GEMM_BIG_MIN_ROWS || !gemm_tc_supported(q->v)) && gemm_big_available())      // prefill rows: reconstruct + tensor-core GEMM (q_gemm.cu:233-266)
+    // prefill rows: reconstruct + tensor-core GEMM (q_gemm.cu:233-266).  9..16 rows would be two 8-row passes of the tcgen05 kernel: on
+    // matrices up to ~20 M weights the dense path is already faster there (4096 x 4096 at 16 rows: 28 us vs 37 us, reference 31 us)
+    const bool small_two_pass = m > GEMV_MTOK && (long long)q->v.K * q->v.N <= 20ll * 1000 * 1000;
+    if ((m > GEMM_BIG_MIN_ROWS || small_two_pass || !gemm_tc_supported(q->v)) && gemm_big_available())
         return gemm_big_launch(q, (const half*)a, lda, (half*)c, ldc, m, clear ? 1 : 0, (cudaStream_t)stream);
     GemvMat mt = {};
     mt.w = q->v;
