@@ -13,17 +13,22 @@
 //
 // Why this shape: a decode step is a chain of ~160 DEPENDENT launches of 8-45 MB each; what bounds it is the serial latency
 // of every launch (measured with the phase stamps below), not instruction throughput.  So:
-//   * one CTA per SM, 16 warps, <= 112 KB of shared memory: TWO consecutive launches are co-resident.  A CTA's first action is
+//   * one CTA per SM, 16 warps, <= 111 KB of shared memory: TWO consecutive launches are co-resident.  A CTA's first action is
 //     griddepcontrol.launch_dependents and every warp requests its first weight stages BEFORE griddepcontrol.wait, so while
-//     launch N computes, launch N+1 is already filling its rings and HBM keeps streaming across the kernel boundary
+//     launch N computes, launch N+1 is already filling its arenas and HBM keeps streaming across the kernel boundary
 //     (5.1 TB/s for a decode-shaped chain of dependent launches vs 3.9 TB/s in plain stream order, tools/ubench/pdlchain.cu).
+//   * every grid is EXACTLY one CTA per SM: CTAs without blocks are slot holders (see the kernel), so no SM ever runs two CTAs
+//     of the same launch while another idles.
 //   * a CTA owns WHOLE 32-column blocks (all of K), its 16 warps split the blocks' K range between them: split-K never leaves
 //     the CTA (shared memory + one barrier), there is no workspace, no atomics, no fence, and summation order is fixed.
-//     The block -> CTA table is computed on the host and travels in the kernel parameters (no divisions on the device).
-//   * a warp streams its block's bytes (tcgen05 layout of layout.h: one contiguous stream per block) with cp.async.bulk into a
-//     private 3-stage ring and never synchronises with another warp in the main loop.
+//   * everything positional (block -> CTA partition, every warp's stage list, who holds partial sums of which block) is a
+//     launch PLAN built on the host once per matrix structure (I8Plan below): the device walks 16-byte descriptors.
+//   * a warp streams its share of a block's bytes (layout.h: one contiguous stream per block) with cp.async.bulk into a
+//     private byte arena (a ring of variable-size stages placed by the host) and never synchronises with another warp in the
+//     main loop; per quantisation group one fp32 FMA with a scale read from the matrix' dense scale table (QMatrix::wtab).
 //   * when the producer of the row scattered a copy in this matrix's stored-row order (I8Out::c_perm), the prologue reads the
 //     row with one 16-byte load per thread instead of eight 2-byte gathers.
+// Measured history of these choices: profiles/r02_history.md.
 #include <string.h>
 
 #include <algorithm>
