@@ -335,3 +335,52 @@ def test_stage_lists(name, N, KS, regions, warps, slot):
         if ps:
             assert (int(red[blk]) >> 16) & 1 == ps[0][1] and all(sl == 0 for (_, sl) in ps[1:])
             assert [w for (w, _) in ps] == sorted(w for (w, _) in ps)
+
+
+# ---- row quantisation ------------------------------------------------------------------------------------------------------
+# gemv_i8.cu stage_round, restated in numpy: per 128-k block the row becomes 16-bit integers with a power-of-two scale whose
+# exponent is taken from max * (1 + 2^-15); rounding is done by the fp32 adder (x * inv + 1.5 * 2^23, low 16 bits = int16).
+
+
+def quantise_block(f):
+    """f: 128 float32 values -> (int array q, float32 scale) exactly as the kernel computes them."""
+    f = f.astype(np.float32)
+    amax = np.float32(np.max(np.abs(f)))
+    if amax == 0:
+        return np.zeros(128, dtype=np.int64), np.float32(0)
+    ef = (np.float32(amax * np.float32(1.000030518)).view(np.uint32) >> 23) & 0xFF
+    inv = np.uint32((268 - int(ef)) << 23).view(np.float32)
+    bits = (f * inv + np.float32(12582912.0)).astype(np.float32).view(np.uint32)           # fma in the kernel: x * inv is exact (power of two)
+    q = (bits & 0xFFFF).astype(np.int64)
+    q = np.where(q >= 32768, q - 65536, q)
+    scale = np.uint32((int(ef) - 14) << 23).view(np.float32)
+    return q, scale
+
+
+def test_row_quantisation_range_and_rounding():
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        f = rng.standard_normal(128).astype(np.float32) * np.float32(10.0 ** rng.uniform(-6, 4))
+        if trial % 3 == 0:      # adversarial maxima: mantissas at the top of a binade (would round up to 2^15 without the bump)
+            f[rng.integers(128)] = np.float32(np.nextafter(np.float32(2.0 ** rng.integers(-20, 15)), np.float32(0)))
+        q, scale = quantise_block(f)
+        assert q.min() >= -32767 and q.max() <= 32767, "int16 high byte must keep its sign"
+        amax = np.max(np.abs(f))
+        assert np.max(np.abs(q)) >= 8192, "the block maximum uses at least 14 bits"
+        # round-to-nearest-even of x / scale, error <= half a step = 2^-15 .. 2^-14 of the block maximum
+        ref = np.rint(f.astype(np.float64) / float(scale)).astype(np.int64)
+        assert np.array_equal(q, ref)
+        assert np.max(np.abs(q * float(scale) - f.astype(np.float64))) <= 0.5 * float(scale) * (1 + 1e-12)
+        assert 0.5 * float(scale) <= amax * 2.0 ** -14
+
+
+def test_row_quantisation_exact_for_fp16_within_16x_of_the_maximum():
+    """fp16 inputs within a factor 16 of their block's maximum are represented exactly (an 11-bit significand fits above the 2^-14
+    step): a unit-vector row therefore returns reconstruct()'s fp16 weights bit for bit."""
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        e = rng.integers(-8, 8)
+        f = (rng.uniform(1.0 / 16, 1.0, 128) * rng.choice([-1, 1], 128) * 2.0 ** e).astype(np.float16).astype(np.float32)
+        f[0] = np.float32(np.float16(2.0 ** e * 0.999))
+        q, scale = quantise_block(f)
+        assert np.array_equal((q * float(scale)).astype(np.float32), f)
